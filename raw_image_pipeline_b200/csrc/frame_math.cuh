@@ -1,0 +1,150 @@
+// Neighbourhood / per-frame arithmetic shared by the sm_100a kernels and the CPU-only test
+// harness (tests/hostsim): bilinear demosaic, cv::remap fixed-point bilinear, and the PCA
+// white-balance solve.  See pixel_math.cuh for the host/device convention.
+#pragma once
+#include "pixel_math.cuh"
+
+namespace rip {
+
+// CFA phase: bit0 = column parity of the R sites, bit1 = row parity of the R sites.
+//   bayer_rggb8 -> 0 (R at (0,0));  bayer_grbg8 -> 1 (R at (0,1));
+//   bayer_gbrg8 -> 2 (R at (1,0));  bayer_bggr8 -> 3 (R at (1,1)).      
+enum : int { CFA_RGGB = 0, CFA_GRBG = 1, CFA_GBRG = 2, CFA_BGGR = 3 };
+
+// ---- bilinear demosaic at one site: debayer.cpp:45-79 == cv::demosaicing + R/B swap ------
+// out(y,x) = interior formula evaluated at (clamp(y,1,H-2), clamp(x,1,W-2)) -- reproduces
+// OpenCV's "copy the neighbouring interior pixel into the border" rule without copy passes.
+RIP_HD void demosaic_at(const uint8_t* raw, int rows, int cols, size_t pitch, int y, int x, int cfa,
+                        int& b, int& g, int& r) {
+  y = y < 1 ? 1 : (y > rows - 2 ? rows - 2 : y);
+  x = x < 1 ? 1 : (x > cols - 2 ? cols - 2 : x);
+  const uint8_t* p = raw + (size_t)y * pitch + x;
+  const uint8_t* pn = p - pitch;
+  const uint8_t* ps = p + pitch;
+  const int c = p[0];
+  const bool row_has_r = ((y & 1) == ((cfa >> 1) & 1));
+  const bool col_is_r = ((x & 1) == (cfa & 1));
+  // colour (non-green) site <=> (row_has_r && col_is_r) || (!row_has_r && !col_is_r)
+  if (row_has_r == col_is_r) {
+    const int cross = (pn[0] + ps[0] + p[-1] + p[1] + 2) >> 2;
+    const int diag = (pn[-1] + pn[1] + ps[-1] + ps[1] + 2) >> 2;
+    g = cross;
+    if (row_has_r) { r = c; b = diag; } else { b = c; r = diag; }
+  } else {
+    const int horiz = (p[-1] + p[1] + 1) >> 1;
+    const int vert = (pn[0] + ps[0] + 1) >> 1;
+    g = c;
+    if (row_has_r) { r = horiz; b = vert; } else { b = horiz; r = vert; }
+  }
+}
+
+// ---- four horizontally adjacent sites x..x+3 (x % 4 == 0) from three rows of packed words --
+// w[row][0] = bytes x-4..x-1, w[row][1] = bytes x..x+3, w[row][2] = bytes x+4..x+7; rows are
+// y-1, y, y+1.  Valid only when all four sites are interior columns (1 <= x, x+3 <= W-2) and the
+// row has already been clamped by the caller.  `cpar` = column parity of the colour sites in
+// this row, `row_has_r` as above.  Results are bit-identical to demosaic_at().
+RIP_HD void demosaic_quad(const uint32_t w[3][3], bool row_has_r, int cpar, int b[4], int g[4], int r[4]) {
+  int n[6], c[6], s[6];  // columns x-1 .. x+4
+  n[0] = w[0][0] >> 24; c[0] = w[1][0] >> 24; s[0] = w[2][0] >> 24;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    n[k + 1] = (w[0][1] >> (8 * k)) & 255;
+    c[k + 1] = (w[1][1] >> (8 * k)) & 255;
+    s[k + 1] = (w[2][1] >> (8 * k)) & 255;
+  }
+  n[5] = w[0][2] & 255; c[5] = w[1][2] & 255; s[5] = w[2][2] & 255;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = k + 1;
+    if ((k & 1) == cpar) {
+      const int cross = (n[i] + s[i] + c[i - 1] + c[i + 1] + 2) >> 2;
+      const int diag = (n[i - 1] + n[i + 1] + s[i - 1] + s[i + 1] + 2) >> 2;
+      g[k] = cross;
+      if (row_has_r) { r[k] = c[i]; b[k] = diag; } else { b[k] = c[i]; r[k] = diag; }
+    } else {
+      const int horiz = (c[i - 1] + c[i + 1] + 1) >> 1;
+      const int vert = (n[i] + s[i] + 1) >> 1;
+      g[k] = c[i];
+      if (row_has_r) { r[k] = horiz; b[k] = vert; } else { b[k] = horiz; r[k] = vert; }
+    }
+  }
+}
+
+// ---- flip.cpp:37-58 as an index map: source coordinate of output pixel (oy, ox) ----------
+// angle 90: out(y,x)=in(H-1-x, y); 180: in(H-1-y, W-1-x); 270: in(x, W-1-y)   
+RIP_HD void flip_source(int angle, int rows, int cols, int oy, int ox, int& iy, int& ix) {
+  if (angle == 90) { iy = rows - 1 - ox; ix = oy; }
+  else if (angle == 180) { iy = rows - 1 - oy; ix = cols - 1 - ox; }
+  else if (angle == 270) { iy = ox; ix = cols - 1 - oy; }
+  else { iy = oy; ix = ox; }
+}
+
+// ---- cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) on 8UC{1,3}: undistortion.cpp:240-245 ----
+template <int CH>
+RIP_HD void remap_pixel(const uint8_t* src, int rows, int cols, size_t pitch, float mx, float my, int out[CH]) {
+  const int sx = remap_fix(mx), sy = remap_fix(my);
+  const int ix = sx >> 5, iy = sy >> 5;
+  const int ax = sx & 31, ay = sy & 31;
+  const int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32;
+  const int w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+  const bool x0 = (unsigned)ix < (unsigned)cols, x1 = (unsigned)(ix + 1) < (unsigned)cols;
+  const bool y0 = (unsigned)iy < (unsigned)rows, y1 = (unsigned)(iy + 1) < (unsigned)rows;
+  const uint8_t* p0 = src + (long long)iy * (long long)pitch + (long long)ix * CH;
+  const uint8_t* p1 = p0 + pitch;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    int acc = 16384;
+    if (y0 && x0) acc += w00 * p0[c];
+    if (y0 && x1) acc += w01 * p0[CH + c];
+    if (y1 && x0) acc += w10 * p1[c];
+    if (y1 && x1) acc += w11 * p1[CH + c];
+    out[c] = clamp_u8(acc >> 15);
+  }
+}
+
+// ---- PCA white balance: white_balance.cpp:73-136 ----------------------------
+// stats = { sum_b, sum_b2, sum_r, sum_r2, sum_g, max_b, max_g, max_r } as exact integers.
+// Eigen::Matrix2f inverse (fixed-size closed form, fp32, no FMA) then the per-pixel
+// addWeighted -> threshold(TRUNC 255) -> convertTo(CV_8U), tabulated for all 256 inputs.
+struct PcaCoeff { float alpha_b, beta_b, alpha_r, beta_r; };
+
+RIP_HD void pca_solve2(float s2, float s1, float m2, float m1, float v0, float v1, float& alpha, float& beta) {
+  const float det = RIP_FSUB(RIP_FMUL(s2, m1), RIP_FMUL(m2, s1));
+  const float invdet = 1.0f / det;  // IEEE division on both host and device
+  const float i00 = RIP_FMUL(m1, invdet), i01 = RIP_FMUL(-s1, invdet);
+  const float i10 = RIP_FMUL(-m2, invdet), i11 = RIP_FMUL(s2, invdet);
+  alpha = RIP_FADD(RIP_FMUL(i00, v0), RIP_FMUL(i01, v1));
+  beta = RIP_FADD(RIP_FMUL(i10, v0), RIP_FMUL(i11, v1));
+}
+
+RIP_HD PcaCoeff pca_coefficients(const unsigned long long* st) {
+  PcaCoeff c;
+  // cv::sum / cv::minMaxLoc return doubles holding exact integers; Eigen's `<<` narrows to float
+  const float sum_b = (float)(double)st[0], sum_b2 = (float)(double)st[1];
+  const float sum_r = (float)(double)st[2], sum_r2 = (float)(double)st[3];
+  const float sum_g = (float)(double)st[4];
+  const float max_b = (float)st[5], max_g = (float)st[6], max_r = (float)st[7];
+  const float max_b2 = (float)(st[5] * st[5]), max_r2 = (float)(st[7] * st[7]);
+  pca_solve2(sum_b2, sum_b, max_b2, max_b, sum_g, max_g, c.alpha_b, c.beta_b);
+  pca_solve2(sum_r2, sum_r, max_r2, max_r, sum_g, max_g, c.alpha_r, c.beta_r);
+  return c;
+}
+
+// cv::addWeighted(x^2, alpha, x, beta, 0) on CV_32F accumulates in double and rounds once;
+// x^2*alpha and x*beta are exact in double (16+24 bits), so a plain double mul/add suffices.
+RIP_HD int pca_lut_entry(int x, float alpha, float beta) {
+#if defined(__CUDA_ARCH__)
+  const double acc = __dadd_rn(__dmul_rn((double)(x * x), (double)alpha), __dmul_rn((double)x, (double)beta));
+#else
+  const double acc = (double)(x * x) * (double)alpha + (double)x * (double)beta;
+#endif
+  float y = (float)acc;
+  if (y > 255.0f) y = 255.0f;  // THRESH_TRUNC (NaN stays NaN -> 0)
+  return sat_u8_rint(y);
+}
+
+// ccc.cpp:383-386: cv::multiply(u8 image, Scalar(gain_b_, gain_g_, gain_r_)) with float gains
+// widened to double -> saturate_cast<uchar>((double)x * (double)gain)  (see enhance())
+RIP_HD int gain_lut_entry(int x, float gain) { return enh_gain_lut_entry(x, (double)gain); }
+
+}  // namespace rip

@@ -1,0 +1,184 @@
+"""CPU-only: the kernels' per-pixel arithmetic (host build of pixel_math.cuh/frame_math.cuh)
+against cv2, exhaustively where the domain is finite (SURVEY 8c 'self-made known-answer tests')."""
+import ctypes
+
+import cv2
+import numpy as np
+import pytest
+
+from conftest import CC_EXAMPLE, cube
+from oracle import cv2_oracle as O
+
+P = ctypes.c_void_p
+
+
+def _run3(fn, img):
+    out = np.empty_like(img)
+    fn(ctypes.c_long(img.shape[0] * img.shape[1]), P(img.ctypes.data), P(out.ctypes.data))
+    return out
+
+
+@pytest.mark.parametrize("name,code", [("hs_bgr2lab", cv2.COLOR_BGR2Lab), ("hs_lab2bgr", cv2.COLOR_Lab2BGR),
+                                       ("hs_bgr2hsv", cv2.COLOR_BGR2HSV), ("hs_hsv2bgr", cv2.COLOR_HSV2BGR)])
+def test_colour_conversions_exhaustive(hostsim, name, code):
+    img = cube()
+    got = _run3(getattr(hostsim, name), img)
+    ref = cv2.cvtColor(img, code)
+    assert int((got != ref).sum()) == 0
+
+
+def _chain(hostsim, stages, img, mask=None, cc=None, bias=(0, 0, 0), enh=(1, 1, 1), wb=None, gamma=None):
+    n = img.shape[0] * img.shape[1]
+    cc = np.asarray(cc if cc is not None else np.eye(3).ravel(), np.float64).astype(np.float32)
+    bias = np.asarray(bias, np.float64).astype(np.float32)
+    enh = np.asarray(enh, np.float64)
+    wb = np.ascontiguousarray(wb if wb is not None else np.tile(np.arange(256, dtype=np.uint8), 3))
+    gamma = np.ascontiguousarray(gamma if gamma is not None else np.arange(256, dtype=np.uint8))
+    out = np.empty_like(img)
+    m = None if mask is None else np.ascontiguousarray(mask, np.float32)
+    hostsim.hs_chain(ctypes.c_uint(stages), ctypes.c_long(n), P(img.ctypes.data),
+                     P(m.ctypes.data) if m is not None else None, P(cc.ctypes.data), P(bias.ctypes.data),
+                     P(enh.ctypes.data), P(wb.ctypes.data), P(gamma.ctypes.data), P(out.ctypes.data))
+    return out
+
+
+@pytest.mark.parametrize("matrix,bias", [(CC_EXAMPLE, (0, 0, 0)),
+                                         ([1.6016861, -1.0104847, 0.2213647, -0.012442476, 1.0841908, -0.07573348,
+                                           0.09123942, -0.8107389, 1.8687756], (3.25, -7.5, 0.49))])
+def test_colour_calibration_exhaustive(hostsim, matrix, bias):
+    img = cube()
+    got = _chain(hostsim, 2, img, cc=matrix, bias=bias)
+    ref = O.color_calibration(img, matrix, bias)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("gains", [(1.0, 1.2, 1.0), (1.0, 1.5, 1.0), (1.1, 0.8, 1.3), (1.5, 2.0, 0.7)])
+def test_enhancer_exhaustive(hostsim, gains):
+    img = cube()
+    got = _chain(hostsim, 16, img, enh=gains)
+    ref = O.color_enhancer(img, *gains)
+    assert int((got != ref).sum()) == 0
+
+
+def test_vignetting_stage(hostsim, oracle_built):
+    rng = np.random.default_rng(5)
+    rows, cols = 540, 720
+    img = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    for (s, a2, a4) in [(1.5, 1e-3, 1e-6), (0.7, 2e-3, 0.0), (3.0, 1e-4, 1e-7)]:
+        mask = O.vignetting_mask(rows, cols, s, a2, a4)
+        got = _chain(hostsim, 8, img, mask=mask)
+        ref = O.vignetting(img, mask)
+        assert int((got != ref).sum()) == 0
+
+
+def test_vignetting_L_times_mask_dense(hostsim):
+    """2M colour triples x random mask values in the range the mask can take."""
+    img = cube()[:512]
+    rng = np.random.default_rng(7)
+    mask = rng.uniform(1.0, 2.6, img.shape[:2]).astype(np.float32)
+    got = _chain(hostsim, 8, img, mask=mask)
+    ref = O.vignetting(img, mask)
+    assert int((got != ref).sum()) == 0
+
+
+def test_gamma_and_full_chain_random(hostsim, oracle_built):
+    rng = np.random.default_rng(11)
+    rows, cols = 480, 640
+    img = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    mask = O.vignetting_mask(rows, cols, 1.5, 1e-3, 1e-6)
+    glut = O.gamma_lut(0.8)
+    wb = np.concatenate([rng.permutation(256).astype(np.uint8), np.arange(256, dtype=np.uint8),
+                         np.sort(rng.integers(0, 256, 256)).astype(np.uint8)])
+    got = _chain(hostsim, 31, img, mask=mask, cc=CC_EXAMPLE, enh=(1.0, 1.2, 1.0), wb=wb, gamma=glut)
+    ref = cv2.merge([cv2.LUT(img[..., 0], wb[:256]), cv2.LUT(img[..., 1], wb[256:512]), cv2.LUT(img[..., 2], wb[512:])])
+    ref = O.color_calibration(ref, CC_EXAMPLE, (0, 0, 0))
+    ref = O.gamma(ref, 0.8)
+    ref = O.vignetting(ref, mask)
+    ref = O.color_enhancer(ref, 1.0, 1.2, 1.0)
+    assert int((got != ref).sum()) == 0
+
+
+CFA_ID = {"bayer_rggb8": 0, "bayer_grbg8": 1, "bayer_gbrg8": 2, "bayer_bggr8": 3}
+
+
+@pytest.mark.parametrize("enc", list(CFA_ID))
+@pytest.mark.parametrize("shape", [(480, 640), (11, 13), (10, 12), (3, 3), (4, 9), (33, 130)])
+@pytest.mark.parametrize("angle", [0, 90, 180, 270])
+def test_demosaic_and_flip(hostsim, enc, shape, angle):
+    rng = np.random.default_rng(abs(hash((enc, shape, angle))) % (1 << 32))
+    raw = rng.integers(0, 256, shape, dtype=np.uint8)
+    ref, _ = O.debayer(raw, enc)
+    ref = O.flip(ref, angle)
+    for mode in (0, 1):
+        out = np.empty(ref.shape, np.uint8)
+        hostsim.hs_demosaic(P(raw.ctypes.data), shape[0], shape[1], CFA_ID[enc], angle, mode, P(out.ctypes.data))
+        assert out.shape == ref.shape
+        assert int((out != ref).sum()) == 0, (enc, shape, angle, mode)
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_remap_random_maps(hostsim, ch):
+    rng = np.random.default_rng(3)
+    rows, cols = 97, 131
+    src = rng.integers(0, 256, (rows, cols, ch) if ch == 3 else (rows, cols), dtype=np.uint8)
+    orows, ocols = 120, 150
+    mx = rng.uniform(-3, cols + 2, (orows, ocols)).astype(np.float32)
+    my = rng.uniform(-3, rows + 2, (orows, ocols)).astype(np.float32)
+    # exact grid points, half-way points, far out-of-range and infinities
+    mx[0, :10] = np.arange(10); my[0, :10] = 5.0
+    mx[1, :10] = np.arange(10) + 0.5; my[1, :10] = 4.5
+    mx[2, :4] = [1e9, -1e9, np.inf, -np.inf]; my[2, :4] = [3, 3, 3, 3]
+    mx[3, :4] = [cols - 1, cols - 1.0 + 1 / 64, cols - 0.5, -0.984375]; my[3, :4] = [rows - 1, rows - 0.5, 0, -0.5]
+    ref = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    out = np.empty_like(ref)
+    hostsim.hs_remap(P(src.ctypes.data), rows, cols, ch, P(mx.ctypes.data), P(my.ctypes.data), orows, ocols,
+                     P(out.ctypes.data))
+    assert int((out != ref).sum()) == 0
+
+
+def test_remap_identity_is_exact():
+    """cv::remap with an identity map returns the image (guards the 32768-weight corner)."""
+    rng = np.random.default_rng(9)
+    src = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
+    xs, ys = np.meshgrid(np.arange(50, dtype=np.float32), np.arange(40, dtype=np.float32))
+    assert np.array_equal(cv2.remap(src, xs, ys, cv2.INTER_LINEAR), src)
+
+
+def _stats(img):
+    b = img[..., 0].astype(np.uint64); g = img[..., 1].astype(np.uint64); r = img[..., 2].astype(np.uint64)
+    return np.array([b.sum(), (b * b).sum(), r.sum(), (r * r).sum(), g.sum(), b.max(), g.max(), r.max()], np.uint64)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pca_lut_matches_oracle(hostsim, seed):
+    rng = np.random.default_rng(seed)
+    rows, cols = 300, 400
+    base = rng.integers(0, 256, (rows, cols, 3)).astype(np.float32)
+    base *= np.array([rng.uniform(0.3, 1.0), rng.uniform(0.5, 1.0), rng.uniform(0.3, 1.0)], np.float32)
+    img = base.astype(np.uint8)
+    st = _stats(img)
+    lut_b = np.empty(256, np.uint8); lut_r = np.empty(256, np.uint8); coeff = np.empty(4, np.float32)
+    hostsim.hs_pca_lut(P(st.ctypes.data), P(lut_b.ctypes.data), P(lut_r.ctypes.data), P(coeff.ctypes.data))
+    (cb, cr), _ = O.pca_coefficients(img)
+    assert coeff[0] == cb[0] and coeff[1] == cb[1] and coeff[2] == cr[0] and coeff[3] == cr[1]
+    ref = O.white_balance_pca(img)
+    got = img.copy()
+    got[..., 0] = lut_b[img[..., 0]]
+    got[..., 2] = lut_r[img[..., 2]]
+    assert np.array_equal(got, ref)
+    # the LUT itself over all 256 inputs (not only the values present in the frame)
+    x = np.arange(256, dtype=np.float32).reshape(1, 256)
+    for lut, (al, be) in ((lut_b, cb), (lut_r, cr)):
+        y = cv2.addWeighted(x * x, float(al), x, float(be), 0.0)
+        _, y = cv2.threshold(y, 255, 255, cv2.THRESH_TRUNC)
+        assert np.array_equal(O.to_u8(y).ravel(), lut)
+
+
+@pytest.mark.parametrize("gain", [1.0, 1.0164, 1.366838, 2.117, 0.9, 3.7, 1.1, 1.3, 0.7])
+def test_gain_lut(hostsim, gain):
+    g = float(np.float32(gain))
+    lut = np.empty(256, np.uint8)
+    hostsim.hs_gain_lut(ctypes.c_float(g), P(lut.ctypes.data))
+    x = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, axis=2)
+    ref = cv2.multiply(x, (g, g, g, 0.0))
+    assert np.array_equal(ref[0, :, 0], lut)
