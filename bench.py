@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""Benchmark of the RAW hot path (BASELINE.json metric: Mpix/s end-to-end at 12 MP full chain;
+fused-kernel HBM GB/s vs peak).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # this framework (B200 kernels)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference's CPU path (cv2 oracle)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, frames sharded (weak scaling)
+
+A "step" is one pass of the hot path over one batch of synthetic Bayer frames: BASELINE.json
+configs[2] = 64 x 4032x3040 bayer_rggb8, full chain (flip 180, pca WB, colour calibration, gamma,
+vignetting, enhancer, undistortion).  `value` = device-resident throughput, `e2e` = the same
+through the host-buffer C-ABI entry point with H2D/D2H copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ROWS, COLS, ENC = 3040, 4032, "bayer_rggb8"
+CC = [2.4276948, 0.21479778, -0.30818, 0.09277014, 1.1962607, -0.09772757, -0.24436986, -0.22239459, 2.099912]
+CALIB_D = [-0.0396482888762527, -0.00367688950406141, 0.00391742438164282, -0.00178738156007817]
+METRIC = "Mpix/s end-to-end at 12MP full chain"
+WORKLOAD = ("BASELINE configs[2]: batch of 4032x3040 bayer_rggb8 frames, full chain = debayer + flip 180 + pca white "
+            "balance + colour calibration (example matrix) + gamma 0.8 + vignetting (1.5,1e-3,1e-6) + HSV enhancer "
+            "(sat 1.2) + fisheye undistortion (balance 0, fov 0.8)")
+
+
+def calib_K(rows, cols):
+    sx, sy = cols / 720.0, rows / 540.0
+    return [347.548139773951 * sx, 0.0, 342.454373227748 * sx, 0.0, 347.434712422309 * sy, 271.368057185649 * sy, 0.0, 0.0, 1.0]
+
+
+def make_pipeline(rows, cols, device=None):
+    from raw_image_pipeline_b200 import RawImagePipeline
+    cfg = os.path.join(ROOT, "raw_image_pipeline_b200", "config")
+    p = RawImagePipeline(False, "", os.path.join(cfg, "alphasense_calib_example.yaml"), "", device=device)
+    p.set_flip(True); p.set_flip_angle(180)
+    p.set_white_balance(True); p.set_white_balance_method("pca")
+    p.set_color_calibration(True); p.set_color_calibration_matrix(CC)
+    p.set_gamma_correction(True); p.set_gamma_correction_method("custom"); p.set_gamma_correction_k(0.8)
+    p.set_vignetting_correction(True); p.set_vignetting_correction_parameters(1.5, 1e-3, 1e-6)
+    p.set_color_enhancer(True); p.set_color_enhancer_saturation_gain(1.2)
+    p.set_undistortion_image_size(cols, rows); p.set_undistortion_camera_matrix(calib_K(rows, cols))
+    p.set_undistortion_distortion_coeffs(CALIB_D); p.set_undistortion_balance(0.0); p.set_undistortion_fov_scale(0.8)
+    p.set_undistortion(True)
+    return p
+
+
+def make_oracle(rows, cols):
+    """The reference's CPU path (call-for-call cv2 replay) -- used ONLY as the timed CPU baseline."""
+    from oracle import cv2_oracle as O
+    op = O.OracleParams(flip_enabled=True, flip_angle=180, wb_enabled=True, wb_method="pca", cc_enabled=True, cc_matrix=CC,
+                        gamma_enabled=True, gamma_k=0.8, vig_enabled=True, enh_enabled=True, enh_saturation_gain=1.2,
+                        und_enabled=True, und_K=calib_K(rows, cols), und_D=CALIB_D, und_width=cols, und_height=rows,
+                        und_balance=0.0, und_fov_scale=0.8)
+    return O.OraclePipeline(op)
+
+
+def make_frames(n, rows, cols, seed0, distinct=16):
+    from raw_image_pipeline_b200 import synth
+    d = min(n, distinct)
+    base = synth.bayer_batch(d, rows, cols, ENC, seed0, "N")
+    if d == n:
+        return base
+    return np.concatenate([base] * ((n + d - 1) // d))[:n]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def time_cpu_reference(rows, cols, n_sample, warm, threads=None):
+    import cv2
+    if threads:
+        cv2.setNumThreads(threads)
+    o = make_oracle(rows, cols)
+    frames = make_frames(n_sample, rows, cols, 3000)
+    for i in range(warm):
+        o.apply(frames[i % n_sample], ENC)
+    t0 = time.perf_counter()
+    for i in range(n_sample):
+        o.apply(frames[i], ENC)
+    dt = time.perf_counter() - t0
+    return n_sample * rows * cols / dt / 1e6, cv2.getNumThreads(), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cv2
+    n_sample = args.ref_frames
+    o = make_oracle(ROWS, COLS)
+    frames = make_frames(n_sample, ROWS, COLS, 3000)
+    for _ in range(args.warmup):
+        o.apply(frames[0], ENC)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for i in range(n_sample):
+            o.apply(frames[i], ENC)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_sample * ROWS * COLS / dt / 1e6
+    cores = cv2.getNumThreads()
+    sample = f"{n_sample} frames of 4032x3040 per step (bounded sample of the 64-frame batch), cv2 {cv2.__version__}, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": n_sample, "distribution": "N"},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, rows, cols = args.frames, ROWS, COLS
+    p = make_pipeline(rows, cols, device=local)
+    frames = make_frames(n, rows, cols, 3000 + 100 * rank)
+    h_in = torch.from_numpy(frames).pin_memory()
+    d_in = h_in.to(dev, non_blocking=True)
+    d_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+
+    def step_device():
+        p.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, ENC, d_out.data_ptr(), host=False, stream=stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = p.kernel_launches()
+    p._set_bool("profile/kernel_events", True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    p._set_bool("profile/kernel_events", False)
+    kernel_ms = p._get_doubles("stats/kernel_ms")
+    launches = p.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n * rows * cols * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, copies inside) ------
+    h_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8).pin_memory()
+
+    def step_host():
+        p.process_batch_ptr(h_in.data_ptr(), n, rows, cols, 1, ENC, h_out.data_ptr(), host=True)
+
+    for _ in range(min(args.warmup, 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = world * n * rows * cols * args.steps / dt_e2e / 1e6
+    # parity spot check of the timed outputs: device batch == host batch for frame 0
+    same = bool(torch.equal(d_out[0].cpu(), h_out[0]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    n_fused = max(kernel_ms[4 + 2], 1.0)
+    fused_ms = kernel_ms[2] / n_fused
+    algo_bytes = 4.0 * n * rows * cols  # 1 B Bayer read + 3 B BGR8 write per pixel
+    achieved = algo_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
+    step_kernel_ms = {k: kernel_ms[i] / args.steps for i, k in enumerate(["pca_stats", "pca_lut", "fused", "remap"])}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch_at_bench_size")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "distribution": "N (natural-ish) + sensor cast",
+                   "l2": f"inputs {n * rows * cols / 1e6:.0f} MB + outputs {3 * n * rows * cols / 1e6:.0f} MB per step >> 126 MB L2 "
+                         "(no flush needed)", "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "kernel_ms_per_step": step_kernel_ms, "device_equals_host_path": same},
+        "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, bayer>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fused_ms,
+                     "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)"},
+        "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * rows * cols) * world,
+                "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "ms_per_step": dt_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, dt = time_cpu_reference(rows, cols, args.cpu_frames, 1)
+        import cv2
+        line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_frames} frames of 4032x3040 through the cv2 call-for-call replay of the "
+                                          f"reference CPU path (cv2 {cv2.__version__}, {cores} threads, {dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU (BASELINE configs[2]: 64)")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames timed for cpu_baseline")
+    ap.add_argument("--ref-frames", type=int, default=4, help="frames per step for --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

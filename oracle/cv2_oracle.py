@@ -237,11 +237,19 @@ class CCC:
 
     def load_model(self, path):  # :116-207
         d = open(path, "rb").read()
-        w, h = struct.unpack("ii", d[:8])
-        a = np.frombuffer(d[8:8 + 8 * w * h], dtype=np.float32)
+        if d[:8] == b"RIPCCC1\0":
+            # this repo's layout (tools/convert_ccc_model.py): same numbers, already transposed
+            w, h = struct.unpack("ii", d[8:16])
+            a = np.frombuffer(d[16:16 + 8 * w * h], dtype=np.float32)
+            self.filter = np.ascontiguousarray(a[:w * h].reshape(h, w))
+            self.bias = np.ascontiguousarray(a[w * h:].reshape(h, w))
+        else:
+            # the reference's model/default.bin: transposed right after reading (:131-132)
+            w, h = struct.unpack("ii", d[:8])
+            a = np.frombuffer(d[8:8 + 8 * w * h], dtype=np.float32)
+            self.filter = np.ascontiguousarray(a[:w * h].reshape(h, w).T)
+            self.bias = np.ascontiguousarray(a[w * h:].reshape(h, w).T)
         self.w, self.h = w, h
-        self.filter = np.ascontiguousarray(a[:w * h].reshape(h, w).T)
-        self.bias = np.ascontiguousarray(a[w * h:].reshape(h, w).T)
         self.filter_fft = cv2.dft(self.filter, flags=0, nonzeroRows=h)
         self.bias_fft = cv2.dft(self.bias, flags=0, nonzeroRows=h)
         self.uv_pos = (h // 2, w // 2)  # cv::Point(x, y)

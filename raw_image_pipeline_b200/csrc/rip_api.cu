@@ -1,0 +1,769 @@
+// C ABI (include/rip_b200.h) + the host pipeline object: owns the parameters (HostState), the
+// device-resident tables, and orchestrates  stats -> LUT -> fused -> remap  per batch of frames.
+// There is no CPU pixel path in this library: without a CUDA device every pixel call fails.
+#include <cuda_runtime.h>
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/rip_b200.h"
+#include "ccc.hpp"
+#include "cv_tables.inc"
+#include "devbuf.hpp"
+#include "frame_math.cuh"
+#include "host_state.hpp"
+#include "kernels.hpp"
+
+#ifndef RIP_DEFAULT_CONFIG_DIR
+#define RIP_DEFAULT_CONFIG_DIR ""
+#endif
+
+using namespace rip;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// per-stream scratch for one in-flight batch
+struct Scratch {
+  DevBuf color;   // pre-undistortion images when the caller does not provide a buffer
+  DevBuf wb;      // n x 768
+  DevBuf stats;   // n x 8 u64
+  DevBuf coeff;   // n x 4 float (pca coefficients, kept for inspection)
+  DevBuf gains;   // n x 3 float (ccc)
+  DevBuf ccc;     // ccc working memory
+  void release() { color.release(); wb.release(); stats.release(); coeff.release(); gains.release(); ccc.release(); }
+};
+
+struct Slot {  // host<->device streaming slot for rip_apply_batch_host
+  cudaStream_t stream = nullptr;
+  DevBuf in, out;
+  Scratch scratch;
+};
+
+struct FrameGeom {
+  int rows, cols, channels;  // input
+  int src, cfa;              // SRC_*, CFA_*
+  int angle;                 // effective flip angle
+  int frows, fcols;          // after flip
+  bool color;                // 3 channels after debayer
+  bool undistort;
+  int orows, ocols, ochannels;  // final
+  std::string out_encoding;
+};
+
+}  // namespace
+
+struct rip_pipeline {
+  HostState hs;
+  std::string last_error;
+  int device = -1;
+  bool cuda_ready = false;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  long long kernel_launches = 0;
+
+  // optional per-kernel timing with CUDA events on the launching stream ("profile/kernel_events")
+  enum { SPAN_STATS = 0, SPAN_LUT = 1, SPAN_FUSED = 2, SPAN_REMAP = 3, SPAN_KINDS = 4 };
+  struct Span { int kind; cudaEvent_t a, b; };
+  bool profile = false;
+  std::vector<Span> spans;
+  cudaError_t span_begin(int kind, cudaStream_t s) {
+    if (!profile) return cudaSuccess;
+    Span sp{kind, nullptr, nullptr};
+    cudaError_t e = cudaEventCreate(&sp.a);
+    if (e == cudaSuccess) e = cudaEventCreate(&sp.b);
+    if (e == cudaSuccess) e = cudaEventRecord(sp.a, s);
+    spans.push_back(sp);
+    return e;
+  }
+  cudaError_t span_end(cudaStream_t s) {
+    if (!profile || spans.empty()) return cudaSuccess;
+    return cudaEventRecord(spans.back().b, s);
+  }
+
+  // device-resident parameters
+  DevBuf d_tables; bool tables_valid = false; double tables_gamma_k = 0; double tables_enh[3] = {0, 0, 0};
+  DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
+  DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
+  std::vector<float> h_map;  // host copy (debug / tests)
+  CccState ccc;
+
+  // single-frame path (rip_apply) state, kept for the getters
+  DevBuf d_in, d_out, d_tmp;
+  Scratch scratch;
+  bool have_frame = false;
+  FrameGeom last_geom{};
+  std::string last_in_encoding;
+  float last_pca[4] = {0, 0, 0, 0};
+
+  std::vector<Slot> slots;
+
+  int fail(int code, const std::string& msg) { last_error = msg; return code; }
+  int cuda_fail(cudaError_t e, const char* what) {
+    return fail(RIP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+};
+
+namespace {
+
+#define RIP_CUDA(p, expr)                                   \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return (p)->cuda_fail(_e, #expr); \
+  } while (0)
+
+int ensure_cuda(rip_pipeline* p) {
+  if (p->cuda_ready) {
+    RIP_CUDA(p, cudaSetDevice(p->device));
+    return RIP_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return p->fail(RIP_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (p->device < 0) {
+    int cur = 0;
+    RIP_CUDA(p, cudaGetDevice(&cur));
+    p->device = cur;
+  }
+  RIP_CUDA(p, cudaSetDevice(p->device));
+  cudaDeviceProp prop;
+  RIP_CUDA(p, cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major < 10)
+    return p->fail(RIP_ERR_CUDA, "device compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                                     " < 10.0: this library is built for sm_100a (B200) only");
+  p->sm_count = prop.multiProcessorCount;
+  RIP_CUDA(p, cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->cuda_ready = true;
+  return RIP_OK;
+}
+
+// debayer.cpp:45-79 + debayer.hpp:74-81: classify the encoding
+int classify_encoding(rip_pipeline* p, const std::string& enc, int channels, int& src, int& cfa, std::string& out_enc) {
+  src = -1; cfa = 0; out_enc = enc;
+  if (enc == "bayer_rggb8") { src = SRC_BAYER; cfa = CFA_RGGB; }
+  else if (enc == "bayer_grbg8") { src = SRC_BAYER; cfa = CFA_GRBG; }
+  else if (enc == "bayer_gbrg8") { src = SRC_BAYER; cfa = CFA_GBRG; }
+  else if (enc == "bayer_bggr8") { src = SRC_BAYER; cfa = CFA_BGGR; }
+  if (src == SRC_BAYER) {
+    if (channels != 1) return p->fail(RIP_ERR_INVALID_ARGUMENT, "Encoding [" + enc + "] needs a 1-channel image");
+    out_enc = "bgr8";
+    return RIP_OK;
+  }
+  if (enc == "rgb8") {
+    if (channels != 3) return p->fail(RIP_ERR_INVALID_ARGUMENT, "Encoding [rgb8] needs a 3-channel image");
+    src = SRC_RGB;  // CPU branch swaps channels but keeps the encoding string (debayer.cpp:72-73)
+    return RIP_OK;
+  }
+  // BAYER_TYPES with the reference's missing comma (debayer.hpp:77-78): these names throw
+  static const char* kListed[] = {"bayer_rggb8bayer_bggr16", "bayer_gbrg16", "bayer_grbg16", "bayer_rggb16"};
+  for (const char* s : kListed)
+    if (enc == s) return p->fail(RIP_ERR_INVALID_ARGUMENT, "Encoding [" + enc + "] is a valid pattern but is not supported!");
+  if (channels == 3) { src = SRC_BGR; return RIP_OK; }
+  return p->fail(RIP_ERR_UNSUPPORTED, "1-channel non-Bayer input (encoding [" + enc + "]) is not supported by this library");
+}
+
+int frame_geometry(rip_pipeline* p, int rows, int cols, int channels, const std::string& enc, FrameGeom& g) {
+  const Params& q = p->hs.p;
+  if (rows < 3 || cols < 3) return p->fail(RIP_ERR_INVALID_ARGUMENT, "image must be at least 3x3");
+  g.rows = rows; g.cols = cols; g.channels = channels;
+  int rc = classify_encoding(p, enc, channels, g.src, g.cfa, g.out_encoding);
+  if (rc != RIP_OK) return rc;
+  g.color = true;
+  g.angle = 0;
+  if (q.flip_enabled && (q.flip_angle == 90 || q.flip_angle == 180 || q.flip_angle == 270)) g.angle = q.flip_angle;
+  const bool swap = (g.angle == 90 || g.angle == 270);
+  g.frows = swap ? cols : rows;
+  g.fcols = swap ? rows : cols;
+  g.undistort = q.und_enabled && q.und_available && q.dist_model != "none";
+  g.orows = g.frows; g.ocols = g.fcols; g.ochannels = 3;
+  if (g.undistort) {
+    if (q.dist_w <= 0 || q.dist_h <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "undistortion enabled without an image size");
+    g.orows = q.dist_h; g.ocols = q.dist_w;  // cv::remap output has the map's size (undistortion.cpp:216,241)
+  }
+  return RIP_OK;
+}
+
+int stage_mask(rip_pipeline* p, const FrameGeom& g, uint32_t& stages, int& wb_kind) {
+  const Params& q = p->hs.p;
+  stages = 0; wb_kind = 0;
+  if (q.wb_enabled && g.color) {  // white_balance.hpp:45-86
+    if (q.wb_method == "pca") wb_kind = 1;
+    else if (q.wb_method == "ccc") wb_kind = 2;
+    else if (q.wb_method == "simple" || q.wb_method == "gray_world" || q.wb_method == "grey_world" || q.wb_method == "learned")
+      return p->fail(RIP_ERR_UNSUPPORTED, "White Balance method [" + q.wb_method +
+                                              "] relies on cv::xphoto and is outside this library's scope; use 'ccc' or 'pca'");
+    else
+      return p->fail(RIP_ERR_INVALID_ARGUMENT, "White Balance method [" + q.wb_method +
+                                                   "] not supported. Supported algorithms: 'simple', 'gray_world', 'learned', 'ccc', 'pca'");
+    stages |= ST_WB;
+  }
+  if (q.cc_enabled && g.color && q.cc_available) stages |= ST_CC;  // color_calibration.hpp:42-56
+  if (q.gamma_enabled) stages |= ST_GAMMA;                          // gamma_correction.hpp:32-43
+  if (q.vig_enabled) stages |= ST_VIG;                              // vignetting_correction.hpp:26-33
+  if (q.enh_enabled && g.color) stages |= ST_ENH;                   // color_enhancer.hpp:33-43
+  return RIP_OK;
+}
+
+int ensure_tables(rip_pipeline* p) {
+  const Params& q = p->hs.p;
+  const double enh[3] = {q.enh_hue_gain, q.enh_saturation_gain, q.enh_value_gain};
+  if (p->tables_valid && p->tables_gamma_k == q.gamma_k && memcmp(enh, p->tables_enh, sizeof enh) == 0) return RIP_OK;
+  std::vector<uint8_t> blob(TABLE_BYTES, 0);
+  build_gamma_lut(q.gamma_k, blob.data() + OFF_GAMMA);
+  build_enhancer_luts(q, blob.data() + OFF_ENH);
+  memcpy(blob.data() + OFF_INVG, kSrgbInvGammaTab, sizeof kSrgbInvGammaTab);
+  memcpy(blob.data() + OFF_SRGBG, kSrgbGammaTab, sizeof kSrgbGammaTab);
+  memcpy(blob.data() + OFF_LABC, kLabCbrtTab, sizeof kLabCbrtTab);
+  memcpy(blob.data() + OFF_YF, kLabToYF, sizeof kLabToYF);
+  memcpy(blob.data() + OFF_SDIV, kHsvSdiv, sizeof kHsvSdiv);
+  memcpy(blob.data() + OFF_HDIV, kHsvHdiv, sizeof kHsvHdiv);
+  RIP_CUDA(p, cudaDeviceSynchronize());  // nothing in flight may still read the old tables
+  RIP_CUDA(p, p->d_tables.reserve(TABLE_BYTES));
+  RIP_CUDA(p, cudaMemcpy(p->d_tables.ptr, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice));
+  p->tables_valid = true; p->tables_gamma_k = q.gamma_k; memcpy(p->tables_enh, enh, sizeof enh);
+  return RIP_OK;
+}
+
+int ensure_vignetting(rip_pipeline* p, int rows, int cols) {
+  const Params& q = p->hs.p;
+  const double par[3] = {q.vig_scale, q.vig_a2, q.vig_a4};
+  if (p->vig_rows == rows && p->vig_cols == cols && memcmp(par, p->vig_par, sizeof par) == 0) return RIP_OK;
+  std::vector<float> quad;
+  int qr = 0, qc = 0;
+  build_vignetting_quadrant(rows, cols, q.vig_scale, q.vig_a2, q.vig_a4, quad, qr, qc);
+  RIP_CUDA(p, cudaDeviceSynchronize());
+  RIP_CUDA(p, p->d_vig.reserve(quad.size() * sizeof(float)));
+  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, quad.data(), quad.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->vig_rows = rows; p->vig_cols = cols; p->vig_pitch = qc; memcpy(p->vig_par, par, sizeof par);
+  return RIP_OK;
+}
+
+void build_host_map(rip_pipeline* p) {
+  const Params& q = p->hs.p;
+  if (p->map_epoch == p->hs.und_epoch && !p->h_map.empty()) return;
+  fisheye_rectify_map(q.dist_K, q.dist_D, q.dist_R, q.rect_K, q.dist_w, q.dist_h, p->h_map);
+  for (float& v : p->h_map)
+    if (v != v) v = -1e9f;  // NaN would round to 0 on the device; make it out-of-range like cvRound(NaN)
+  p->map_w = q.dist_w; p->map_h = q.dist_h;
+}
+
+int ensure_map(rip_pipeline* p) {
+  if (p->map_epoch == p->hs.und_epoch && p->d_map.ptr) return RIP_OK;
+  build_host_map(p);
+  RIP_CUDA(p, cudaDeviceSynchronize());
+  RIP_CUDA(p, p->d_map.reserve(p->h_map.size() * sizeof(float)));
+  RIP_CUDA(p, cudaMemcpy(p->d_map.ptr, p->h_map.data(), p->h_map.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->map_epoch = p->hs.und_epoch;
+  return RIP_OK;
+}
+
+// The pipeline proper, on device memory (raw_image_pipeline.hpp:143-172).
+int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8_t* d_in, size_t in_pitch,
+                   size_t in_frame_stride, int n, uint8_t* d_out, size_t out_frame_stride, uint8_t* d_color_user,
+                   uint32_t stages_override, bool use_override, cudaStream_t stream) {
+  const Params& q = p->hs.p;
+  uint32_t stages = 0;
+  int wb_kind = 0;
+  if (use_override) stages = stages_override;
+  else {
+    int rc = stage_mask(p, g, stages, wb_kind);
+    if (rc != RIP_OK) return rc;
+  }
+  const bool undistort = g.undistort && !use_override;
+  int launches = 0;
+  if (stages & (ST_GAMMA | ST_VIG | ST_ENH)) { int rc = ensure_tables(p); if (rc != RIP_OK) return rc; }
+  if (stages & ST_VIG) { int rc = ensure_vignetting(p, g.frows, g.fcols); if (rc != RIP_OK) return rc; }
+  if (undistort) { int rc = ensure_map(p); if (rc != RIP_OK) return rc; }
+
+  FrameParams fp{};
+  fp.in = d_in; fp.in_frame_stride = (long long)in_frame_stride; fp.in_pitch = (int)in_pitch;
+  fp.rows = g.rows; fp.cols = g.cols; fp.orows = g.frows; fp.ocols = g.fcols; fp.n_frames = n;
+  fp.cfa = g.cfa; fp.angle = g.angle; fp.src = g.src;
+  fp.tables = p->d_tables.as<uint8_t>();
+  fp.vig = p->d_vig.as<float>(); fp.vig_pitch = p->vig_pitch;
+  for (int i = 0; i < 9; ++i) fp.k.cc[i] = q.cc_matrix[i];
+  for (int i = 0; i < 3; ++i) fp.k.cc_bias[i] = (float)q.cc_bias[i];  // Scalar double -> fp32 on cv::add
+  const size_t color_frame = (size_t)g.frows * g.fcols * 3;
+  if (undistort) {
+    if (d_color_user) { fp.out = d_color_user; }
+    else { RIP_CUDA(p, sc.color.reserve(color_frame * n)); fp.out = sc.color.as<uint8_t>(); }
+    fp.out_frame_stride = (long long)color_frame;
+  } else {
+    fp.out = d_out; fp.out_frame_stride = (long long)out_frame_stride;
+  }
+  fp.out_pitch = g.fcols * 3;
+
+  if (stages & ST_WB) {
+    RIP_CUDA(p, sc.wb.reserve((size_t)n * 768));
+    fp.wb = sc.wb.as<uint8_t>();
+    if (wb_kind == 1) {
+      RIP_CUDA(p, sc.stats.reserve((size_t)n * 8 * sizeof(unsigned long long)));
+      RIP_CUDA(p, sc.coeff.reserve((size_t)n * 4 * sizeof(float)));
+      fp.stats = sc.stats.as<unsigned long long>();
+      RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_STATS, stream));
+      RIP_CUDA(p, launch_pca_stats(fp, p->sm_count, stream, &launches));
+      RIP_CUDA(p, p->span_end(stream));
+      RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_LUT, stream));
+      RIP_CUDA(p, launch_pca_lut(fp.stats, sc.wb.as<uint8_t>(), sc.coeff.as<float>(), n, stream, &launches));
+      RIP_CUDA(p, p->span_end(stream));
+    } else {
+      int rc = ccc_white_balance(p->ccc, q, fp, sc.ccc, sc.gains, p->sm_count, stream, &launches, p->last_error);
+      if (rc != RIP_OK) return rc;
+      RIP_CUDA(p, launch_gain_lut(static_cast<const float*>(sc.gains.ptr), sc.wb.as<uint8_t>(), n, stream, &launches));
+    }
+  }
+  RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
+  RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
+  RIP_CUDA(p, p->span_end(stream));
+  if (undistort) {
+    RemapParams rp{};
+    rp.src = fp.out; rp.src_frame_stride = fp.out_frame_stride;
+    rp.rows = g.frows; rp.cols = g.fcols; rp.pitch = g.fcols * 3;
+    rp.dst = d_out; rp.dst_frame_stride = (long long)out_frame_stride;
+    rp.orows = g.orows; rp.ocols = g.ocols; rp.dpitch = g.ocols * 3;
+    rp.n_frames = n;
+    rp.map = p->d_map.as<float2>();
+    RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_REMAP, stream));
+    RIP_CUDA(p, launch_remap(3, rp, stream, &launches));
+    RIP_CUDA(p, p->span_end(stream));
+  }
+  p->kernel_launches += launches;
+  return RIP_OK;
+}
+
+// The reference bakes its default YAML paths from __FILE__ (raw_image_pipeline.cpp:8-12); here
+// they live in `config/` next to the shared library (override: RIP_B200_CONFIG_DIR).
+std::string default_config_dir() {
+  const char* env = getenv("RIP_B200_CONFIG_DIR");
+  if (env && *env) return env;
+  Dl_info info;
+  if (dladdr(reinterpret_cast<const void*>(&rip_device_count), &info) && info.dli_fname) {
+    std::string so = info.dli_fname;
+    const size_t slash = so.rfind('/');
+    return (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/config";
+  }
+  return RIP_DEFAULT_CONFIG_DIR;
+}
+
+int create_common(int use_gpu, rip_pipeline** out, rip_pipeline*& p) {
+  if (!out) { g_create_error = "out is NULL"; return RIP_ERR_INVALID_ARGUMENT; }
+  p = new rip_pipeline();
+  p->hs.p.use_gpu = use_gpu != 0;
+  p->hs.config_dir = default_config_dir();
+  std::string err;
+  if (!ccc_load_model(p->ccc, p->hs.config_dir + "/ccc_model.bin", err)) p->hs.log += "Warning: " + err + "\n";
+  *out = p;
+  return RIP_OK;
+}
+
+bool key_is(const char* key, const char* name) { return strcmp(key, name) == 0; }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int rip_create(int use_gpu, const char* params_path, const char* calibration_path, const char* color_calibration_path,
+               rip_pipeline** out) {
+  rip_pipeline* p = nullptr;
+  int rc = create_common(use_gpu, out, p);
+  if (rc != RIP_OK) return rc;
+  const std::string dir = p->hs.config_dir;
+  // raw_image_pipeline.cpp:23-40
+  p->hs.load_params((params_path && *params_path) ? params_path : dir + "/pipeline_params_example.yaml");
+  if (calibration_path && *calibration_path) p->hs.load_camera_calibration(calibration_path);
+  p->hs.load_color_calibration((color_calibration_path && *color_calibration_path) ? color_calibration_path
+                                                                                   : dir + "/alphasense_color_calib_example.yaml");
+  return RIP_OK;
+}
+
+int rip_create_default(int use_gpu, rip_pipeline** out) {
+  rip_pipeline* p = nullptr;
+  int rc = create_common(use_gpu, out, p);
+  if (rc != RIP_OK) return rc;
+  const std::string dir = p->hs.config_dir;
+  // raw_image_pipeline.cpp:16-21
+  p->hs.load_params(dir + "/pipeline_params_example.yaml");
+  p->hs.load_camera_calibration(dir + "/alphasense_calib_example.yaml");
+  p->hs.load_color_calibration(dir + "/alphasense_color_calib_example.yaml");
+  return RIP_OK;
+}
+
+void rip_destroy(rip_pipeline* p) {
+  if (!p) return;
+  if (p->cuda_ready) {
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    p->d_tables.release(); p->d_vig.release(); p->d_map.release();
+    p->d_in.release(); p->d_out.release(); p->d_tmp.release(); p->scratch.release();
+    ccc_release(p->ccc);
+    for (Slot& s : p->slots) {
+      s.in.release(); s.out.release(); s.scratch.release();
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (p->stream) cudaStreamDestroy(p->stream);
+  }
+  delete p;
+}
+
+const char* rip_last_error(const rip_pipeline* p) { return p ? p->last_error.c_str() : g_create_error.c_str(); }
+
+int rip_load_params(rip_pipeline* p, const char* path) { p->hs.load_params(path ? path : ""); return RIP_OK; }
+int rip_load_camera_calibration(rip_pipeline* p, const char* path) { p->hs.load_camera_calibration(path ? path : ""); return RIP_OK; }
+int rip_load_color_calibration(rip_pipeline* p, const char* path) { p->hs.load_color_calibration(path ? path : ""); return RIP_OK; }
+int rip_init_undistortion(rip_pipeline* p) { p->hs.init_undistortion(); return RIP_OK; }
+int rip_reset_white_balance_temporal_consistency(rip_pipeline* p) {
+  if (p->hs.p.wb_method == "ccc") p->ccc.first_frame = true;  // white_balance.cpp:42-47
+  return RIP_OK;
+}
+
+// ---- setters --------------------------------------------------------------------------------
+int rip_set_bool(rip_pipeline* p, const char* key, int value) {
+  Params& q = p->hs.p;
+  const bool v = value != 0;
+  if (key_is(key, "gpu")) q.use_gpu = v;
+  else if (key_is(key, "debug")) q.debug = v;
+  else if (key_is(key, "profile/kernel_events")) p->profile = v;
+  else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
+  else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
+  else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;
+  else if (key_is(key, "white_balance/temporal_consistency")) q.wb_temporal_consistency = v;
+  else if (key_is(key, "color_calibration/enabled")) q.cc_enabled = v;
+  else if (key_is(key, "gamma_correction/enabled")) q.gamma_enabled = v;
+  else if (key_is(key, "vignetting_correction/enabled")) q.vig_enabled = v;
+  else if (key_is(key, "color_enhancer/enabled")) q.enh_enabled = v;
+  else if (key_is(key, "undistortion/enabled")) q.und_enabled = v;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown bool key: ") + key);
+  return RIP_OK;
+}
+
+int rip_set_int(rip_pipeline* p, const char* key, int value) {
+  if (key_is(key, "flip/angle")) p->hs.p.flip_angle = value;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown int key: ") + key);
+  return RIP_OK;
+}
+
+int rip_set_double(rip_pipeline* p, const char* key, double value) {
+  Params& q = p->hs.p;
+  if (key_is(key, "white_balance/clipping_percentile")) q.wb_clipping_percentile = value;
+  else if (key_is(key, "gamma_correction/k")) q.gamma_k = value;
+  else if (key_is(key, "color_enhancer/hue_gain")) p->hs.set_hue_gain(value);
+  else if (key_is(key, "color_enhancer/saturation_gain")) p->hs.set_saturation_gain(value);
+  else if (key_is(key, "color_enhancer/value_gain")) p->hs.set_value_gain(value);
+  else if (key_is(key, "undistortion/balance")) { q.und_balance = value; p->hs.init_undistortion(); }
+  else if (key_is(key, "undistortion/fov_scale")) { q.und_fov_scale = value; p->hs.init_undistortion(); }
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown double key: ") + key);
+  return RIP_OK;
+}
+
+int rip_set_string(rip_pipeline* p, const char* key, const char* value) {
+  Params& q = p->hs.p;
+  const std::string v = value ? value : "";
+  if (key_is(key, "debayer/encoding")) q.debayer_encoding = v;
+  else if (key_is(key, "white_balance/method")) q.wb_method = v;
+  else if (key_is(key, "gamma_correction/method")) q.gamma_method = v;
+  else if (key_is(key, "undistortion/distortion_model")) p->hs.set_distortion_model(v);
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown string key: ") + key);
+  return RIP_OK;
+}
+
+int rip_set_doubles(rip_pipeline* p, const char* key, const double* v, int n) {
+  Params& q = p->hs.p;
+  auto need = [&](int want) -> int {
+    if (n < want || !v)
+      return p->fail(RIP_ERR_INVALID_ARGUMENT, std::string(key) + " needs " + std::to_string(want) + " values, got " + std::to_string(n));
+    return RIP_OK;
+  };
+  int rc;
+  if (key_is(key, "white_balance/saturation_threshold")) { if ((rc = need(2))) return rc; q.wb_bright_thr = v[0]; q.wb_dark_thr = v[1]; }
+  else if (key_is(key, "color_calibration/matrix")) { if ((rc = need(9))) return rc; for (int i = 0; i < 9; ++i) q.cc_matrix[i] = (float)v[i]; }
+  else if (key_is(key, "color_calibration/bias")) { if ((rc = need(3))) return rc; q.cc_bias[0] = v[0]; q.cc_bias[1] = v[1]; q.cc_bias[2] = v[2]; q.cc_bias[3] = 0; }
+  else if (key_is(key, "vignetting_correction/parameters")) { if ((rc = need(3))) return rc; q.vig_scale = v[0]; q.vig_a2 = v[1]; q.vig_a4 = v[2]; }
+  else if (key_is(key, "undistortion/image_size")) { if ((rc = need(2))) return rc; p->hs.set_image_size((int)v[0], (int)v[1]); }
+  else if (key_is(key, "undistortion/new_image_size")) { if ((rc = need(2))) return rc; p->hs.set_new_image_size((int)v[0], (int)v[1]); }
+  else if (key_is(key, "undistortion/camera_matrix")) { if ((rc = need(9))) return rc; p->hs.set_camera_matrix(v); }
+  else if (key_is(key, "undistortion/distortion_coefficients")) { if ((rc = need(4))) return rc; p->hs.set_distortion_coefficients(v); }
+  else if (key_is(key, "undistortion/rectification_matrix")) { if ((rc = need(9))) return rc; p->hs.set_rectification_matrix(v); }
+  else if (key_is(key, "undistortion/projection_matrix")) { if ((rc = need(12))) return rc; p->hs.set_projection_matrix(v); }
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown doubles key: ") + key);
+  return RIP_OK;
+}
+
+// ---- getters --------------------------------------------------------------------------------
+int rip_get_bool(rip_pipeline* p, const char* key, int* value) {
+  const Params& q = p->hs.p;
+  bool v;
+  if (key_is(key, "gpu")) v = q.use_gpu;
+  else if (key_is(key, "debug")) v = q.debug;
+  else if (key_is(key, "debayer/enabled")) v = q.debayer_enabled;
+  else if (key_is(key, "flip/enabled")) v = q.flip_enabled;
+  else if (key_is(key, "white_balance/enabled")) v = q.wb_enabled;
+  else if (key_is(key, "white_balance/temporal_consistency")) v = q.wb_temporal_consistency;
+  else if (key_is(key, "color_calibration/enabled")) v = q.cc_enabled;
+  else if (key_is(key, "color_calibration/available")) v = q.cc_available;
+  else if (key_is(key, "gamma_correction/enabled")) v = q.gamma_enabled;
+  else if (key_is(key, "vignetting_correction/enabled")) v = q.vig_enabled;
+  else if (key_is(key, "color_enhancer/enabled")) v = q.enh_enabled;
+  else if (key_is(key, "undistortion/enabled")) v = q.und_enabled;
+  else if (key_is(key, "undistortion/available")) v = q.und_available;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown bool key: ") + key);
+  *value = v ? 1 : 0;
+  return RIP_OK;
+}
+
+int rip_get_int(rip_pipeline* p, const char* key, int* value) {
+  const Params& q = p->hs.p;
+  if (key_is(key, "flip/angle")) *value = q.flip_angle;
+  else if (key_is(key, "dist/image_height")) *value = q.dist_h;
+  else if (key_is(key, "dist/image_width")) *value = q.dist_w;
+  else if (key_is(key, "rect/image_height")) *value = q.rect_h;
+  else if (key_is(key, "rect/image_width")) *value = q.rect_w;
+  else if (key_is(key, "stats/kernel_launches")) *value = (int)p->kernel_launches;
+  else if (key_is(key, "stats/ccc_u")) *value = p->ccc.uv_x;
+  else if (key_is(key, "stats/ccc_v")) *value = p->ccc.uv_y;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown int key: ") + key);
+  return RIP_OK;
+}
+
+int rip_get_double(rip_pipeline* p, const char* key, double* value) {
+  const Params& q = p->hs.p;
+  if (key_is(key, "white_balance/clipping_percentile")) *value = q.wb_clipping_percentile;
+  else if (key_is(key, "gamma_correction/k")) *value = q.gamma_k;
+  // *member* values (after the reference's cross-wired setters)
+  else if (key_is(key, "color_enhancer/hue_gain_member")) *value = q.enh_hue_gain;
+  else if (key_is(key, "color_enhancer/saturation_gain_member")) *value = q.enh_saturation_gain;
+  else if (key_is(key, "color_enhancer/value_gain_member")) *value = q.enh_value_gain;
+  else if (key_is(key, "undistortion/balance")) *value = q.und_balance;
+  else if (key_is(key, "undistortion/fov_scale")) *value = q.und_fov_scale;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown double key: ") + key);
+  return RIP_OK;
+}
+
+int rip_get_string(rip_pipeline* p, const char* key, char* value, size_t capacity) {
+  const Params& q = p->hs.p;
+  std::string v;
+  if (key_is(key, "debayer/encoding")) v = q.debayer_encoding;
+  else if (key_is(key, "white_balance/method")) v = q.wb_method;
+  else if (key_is(key, "gamma_correction/method")) v = q.gamma_method;
+  else if (key_is(key, "dist/distortion_model")) v = p->hs.dist_distortion_model();
+  else if (key_is(key, "rect/distortion_model")) v = p->hs.rect_distortion_model();
+  else if (key_is(key, "log")) v = p->hs.log;
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown string key: ") + key);
+  if (!value || capacity < v.size() + 1) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "string buffer too small");
+  memcpy(value, v.c_str(), v.size() + 1);
+  return RIP_OK;
+}
+
+int rip_get_doubles(rip_pipeline* p, const char* key, double* values, int capacity, int* n) {
+  const Params& q = p->hs.p;
+  std::vector<double> v;
+  auto from = [&](const double* s, int c) { v.assign(s, s + c); };
+  if (key_is(key, "color_calibration/matrix")) { for (int i = 0; i < 9; ++i) v.push_back((double)q.cc_matrix[i]); }
+  else if (key_is(key, "color_calibration/bias")) from(q.cc_bias, 4);  // cv::Mat(cv::Scalar) is 4x1
+  else if (key_is(key, "white_balance/saturation_threshold")) { v = {q.wb_bright_thr, q.wb_dark_thr}; }
+  else if (key_is(key, "vignetting_correction/parameters")) { v = {q.vig_scale, q.vig_a2, q.vig_a4}; }
+  else if (key_is(key, "dist/camera_matrix")) from(q.dist_K, 9);
+  else if (key_is(key, "dist/distortion_coefficients")) from(q.dist_D, 4);
+  else if (key_is(key, "dist/rectification_matrix")) from(q.dist_R, 9);
+  else if (key_is(key, "dist/projection_matrix")) from(q.dist_P, 12);
+  else if (key_is(key, "rect/camera_matrix")) from(q.rect_K, 9);
+  else if (key_is(key, "rect/distortion_coefficients")) from(q.rect_D, 4);
+  else if (key_is(key, "rect/rectification_matrix")) from(q.rect_R, 9);
+  else if (key_is(key, "rect/projection_matrix")) from(q.rect_P, 12);
+  else if (key_is(key, "stats/pca_coefficients")) { for (float f : p->last_pca) v.push_back((double)f); }
+  else if (key_is(key, "stats/kernel_ms")) {
+    // {stats, lut, fused, remap} total milliseconds and span counts since the last query; the
+    // caller must have synchronised the stream(s) the work was enqueued on
+    v.assign(2 * rip_pipeline::SPAN_KINDS, 0.0);
+    for (auto& sp : p->spans) {
+      float ms = 0.f;
+      if (sp.a && sp.b && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+        v[sp.kind] += ms; v[rip_pipeline::SPAN_KINDS + sp.kind] += 1.0;
+      }
+      if (sp.a) cudaEventDestroy(sp.a);
+      if (sp.b) cudaEventDestroy(sp.b);
+    }
+    p->spans.clear();
+  }
+  else if (key_is(key, "stats/ccc_gains")) { v = {(double)p->ccc.gain_b, (double)p->ccc.gain_g, (double)p->ccc.gain_r}; }
+  else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown doubles key: ") + key);
+  if (n) *n = (int)v.size();
+  if (!values || capacity < (int)v.size()) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "doubles buffer too small");
+  for (size_t i = 0; i < v.size(); ++i) values[i] = v[i];
+  return RIP_OK;
+}
+
+// host tables for inspection / CPU-side tests (no GPU needed)
+int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void* out, size_t capacity, size_t* bytes) {
+  std::vector<uint8_t> data;
+  if (key_is(name, "gamma_lut")) { data.resize(256); build_gamma_lut(p->hs.p.gamma_k, data.data()); }
+  else if (key_is(name, "enhancer_luts")) { data.resize(768); build_enhancer_luts(p->hs.p, data.data()); }
+  else if (key_is(name, "vignetting_mask")) {  // expanded to the full rows x cols mask
+    std::vector<float> q; int qr, qc;
+    build_vignetting_quadrant(rows, cols, p->hs.p.vig_scale, p->hs.p.vig_a2, p->hs.p.vig_a4, q, qr, qc);
+    data.resize((size_t)rows * cols * 4);
+    float* m = reinterpret_cast<float*>(data.data());
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < cols; ++j) m[(size_t)i * cols + j] = q[(size_t)(std::abs(2 * i - rows) >> 1) * qc + (std::abs(2 * j - cols) >> 1)];
+  } else if (key_is(name, "undistortion_map")) {  // interleaved (x, y), dist_h x dist_w
+    build_host_map(p);
+    data.resize(p->h_map.size() * 4);
+    memcpy(data.data(), p->h_map.data(), data.size());
+  } else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown table: ") + name);
+  if (bytes) *bytes = data.size();
+  if (!out || capacity < data.size()) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "table buffer too small");
+  memcpy(out, data.data(), data.size());
+  return RIP_OK;
+}
+
+// ---- frames ---------------------------------------------------------------------------------
+int rip_output_shape(rip_pipeline* p, int rows, int cols, int channels, const char* encoding, int* out_rows, int* out_cols,
+                     int* out_channels) {
+  FrameGeom g;
+  int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
+  if (rc != RIP_OK) return rc;
+  if (out_rows) *out_rows = g.orows;
+  if (out_cols) *out_cols = g.ocols;
+  if (out_channels) *out_channels = g.ochannels;
+  return RIP_OK;
+}
+
+int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int channels, size_t step, char* encoding,
+              size_t encoding_capacity, uint8_t* out, size_t out_capacity, int* out_rows, int* out_cols, int* out_channels) {
+  if (!data || !out || !encoding) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument");
+  FrameGeom g;
+  int rc = frame_geometry(p, rows, cols, channels, encoding, g);
+  if (rc != RIP_OK) return rc;
+  uint32_t st; int wbk;
+  if ((rc = stage_mask(p, g, st, wbk)) != RIP_OK) return rc;
+  const size_t out_bytes = (size_t)g.orows * g.ocols * g.ochannels;
+  if (out_capacity < out_bytes) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "output buffer too small");
+  if (g.out_encoding.size() + 1 > encoding_capacity) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "encoding buffer too small");
+  if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
+  const size_t row_bytes = (size_t)cols * channels;
+  const size_t pitch = (row_bytes + 15) & ~(size_t)15;
+  RIP_CUDA(p, p->d_in.reserve(pitch * rows));
+  RIP_CUDA(p, p->d_out.reserve(out_bytes));
+  RIP_CUDA(p, cudaMemcpy2DAsync(p->d_in.ptr, pitch, data, step ? step : row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, p->stream));
+  rc = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * rows, 1, p->d_out.as<uint8_t>(), out_bytes, nullptr, 0,
+                      false, p->stream);
+  if (rc != RIP_OK) return rc;
+  RIP_CUDA(p, cudaMemcpyAsync(out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+  if (wbk == 1) RIP_CUDA(p, cudaMemcpyAsync(p->last_pca, p->scratch.coeff.ptr, sizeof p->last_pca, cudaMemcpyDeviceToHost, p->stream));
+  RIP_CUDA(p, cudaStreamSynchronize(p->stream));
+  p->have_frame = true; p->last_geom = g; p->last_in_encoding = encoding;
+  memcpy(encoding, g.out_encoding.c_str(), g.out_encoding.size() + 1);
+  if (out_rows) *out_rows = g.orows;
+  if (out_cols) *out_cols = g.ocols;
+  if (out_channels) *out_channels = g.ochannels;
+  return RIP_OK;
+}
+
+int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity, int* rows, int* cols, int* channels) {
+  auto shape = [&](int r, int c, int ch) { if (rows) *rows = r; if (cols) *cols = c; if (channels) *channels = ch; };
+  if (which == RIP_IMAGE_RECT_MASK || !p->have_frame) { shape(0, 0, 0); return RIP_OK; }  // undistortion.hpp:136 never written
+  const FrameGeom& g = p->last_geom;
+  int rc = ensure_cuda(p);
+  if (rc != RIP_OK) return rc;
+  const uint8_t* src = nullptr;
+  int r = 0, c = 0;
+  if (which == RIP_IMAGE_PROCESSED) { src = p->d_out.as<uint8_t>(); r = g.orows; c = g.ocols; }
+  else if (which == RIP_IMAGE_DIST_COLOR) {
+    src = g.undistort ? p->scratch.color.as<uint8_t>() : p->d_out.as<uint8_t>(); r = g.frows; c = g.fcols;
+  } else if (which == RIP_IMAGE_DIST_DEBAYERED) {
+    // FlipModule's snapshot (flip.hpp:36-45): recomputed on demand from the retained input
+    r = g.frows; c = g.fcols;
+    const size_t bytes = (size_t)r * c * 3;
+    RIP_CUDA(p, p->d_tmp.reserve(bytes));
+    const size_t pitch = (((size_t)g.cols * g.channels) + 15) & ~(size_t)15;
+    Scratch dummy;
+    rc = process_device(p, dummy, g, p->d_in.as<uint8_t>(), pitch, pitch * g.rows, 1, p->d_tmp.as<uint8_t>(), bytes, nullptr, 0, true,
+                        p->stream);
+    if (rc != RIP_OK) return rc;
+    src = p->d_tmp.as<uint8_t>();
+  } else return p->fail(RIP_ERR_INVALID_ARGUMENT, "unknown image id");
+  shape(r, c, 3);
+  const size_t bytes = (size_t)r * c * 3;
+  if (!out || out_capacity < bytes) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "image buffer too small");
+  RIP_CUDA(p, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, p->stream));
+  RIP_CUDA(p, cudaStreamSynchronize(p->stream));
+  return RIP_OK;
+}
+
+int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame_stride, int n_frames, int rows, int cols,
+                           int channels, const char* encoding, uint8_t* d_out, size_t out_frame_stride, uint8_t* d_dist_color,
+                           void* cuda_stream) {
+  if (!d_in || !d_out || n_frames <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument or empty batch");
+  FrameGeom g;
+  int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
+  if (rc != RIP_OK) return rc;
+  if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
+  const size_t pitch = (size_t)cols * channels;
+  if (in_frame_stride < pitch * rows) return p->fail(RIP_ERR_INVALID_ARGUMENT, "in_frame_stride smaller than a frame");
+  if (out_frame_stride < (size_t)g.orows * g.ocols * 3) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
+  return process_device(p, p->scratch, g, d_in, pitch, in_frame_stride, n_frames, d_out, out_frame_stride, d_dist_color, 0, false,
+                        static_cast<cudaStream_t>(cuda_stream));
+}
+
+int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames, int rows, int cols,
+                         int channels, const char* encoding, uint8_t* out, size_t out_frame_stride) {
+  if (!in || !out || n_frames <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument or empty batch");
+  FrameGeom g;
+  int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
+  if (rc != RIP_OK) return rc;
+  if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
+  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * 3;
+  if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
+  // chunk so that copies of chunk i+1 / i-1 overlap the kernels of chunk i
+  const int kSlots = 3;
+  int chunk = (int)((48u << 20) / (in_frame + out_frame));
+  chunk = chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
+  if (p->slots.size() < (size_t)kSlots) {
+    const size_t old = p->slots.size();
+    p->slots.resize(kSlots);
+    for (size_t i = old; i < p->slots.size(); ++i) RIP_CUDA(p, cudaStreamCreateWithFlags(&p->slots[i].stream, cudaStreamNonBlocking));
+  }
+  // temporal CCC state is a per-stream recurrence: keep chunks in order on the host side
+  int slot_i = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, slot_i = (slot_i + 1) % kSlots) {
+    const int n = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+    Slot& s = p->slots[slot_i];
+    RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again
+    RIP_CUDA(p, s.in.reserve(in_frame * n));
+    RIP_CUDA(p, s.out.reserve(out_frame * n));
+    RIP_CUDA(p, cudaMemcpy2DAsync(s.in.ptr, in_frame, in + (size_t)f0 * in_frame_stride, in_frame_stride, in_frame, n,
+                                  cudaMemcpyHostToDevice, s.stream));
+    rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels, in_frame, n, s.out.as<uint8_t>(), out_frame,
+                        nullptr, 0, false, s.stream);
+    if (rc != RIP_OK) return rc;
+    RIP_CUDA(p, cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_frame_stride, s.out.ptr, out_frame, out_frame, n,
+                                  cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (Slot& s : p->slots) RIP_CUDA(p, cudaStreamSynchronize(s.stream));
+  return RIP_OK;
+}
+
+int rip_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+  return n;
+}
+
+int rip_set_device(rip_pipeline* p, int device) {
+  if (p->cuda_ready) return p->fail(RIP_ERR_INVALID_ARGUMENT, "device already selected");
+  p->device = device;
+  return RIP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""CPU-only: the C-ABI library loads, exports every declared symbol, and its host logic
+(YAML loading, setter semantics, host-computed tables) matches the reference / the oracle.
+No pixel work happens here (that needs the GPU and is covered by test_gpu_parity.py)."""
+import os
+import re
+
+import cv2
+import numpy as np
+import pytest
+
+from conftest import CALIB_720, ROOT, scaled_calib
+from oracle import cv2_oracle as O
+from raw_image_pipeline_b200 import RawImagePipeline, RawImagePipelineError
+from raw_image_pipeline_b200 import _lib as L
+
+CONFIG = os.path.join(ROOT, "raw_image_pipeline_b200", "config")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rip_b200.h")).read()
+    declared = set(re.findall(r"RIP_API\s+[\w\s\*]+?\b(rip_\w+)\s*\(", header))
+    assert len(declared) >= 27
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = RawImagePipeline(False, "", "", "")
+    with pytest.raises(RawImagePipelineError) as e:
+        p.process(np.zeros((16, 16), np.uint8), "bayer_rggb8")
+    assert e.value.code == L.RIP_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_default_constructor_matches_reference_defaults():
+    p = RawImagePipeline(False)  # raw_image_pipeline.cpp:16-21 + config/pipeline_params_example.yaml
+    assert p.is_debayer_enabled() and not p.is_flip_enabled() and p.is_white_balance_enabled()
+    assert not p.is_color_calibration_enabled() and not p.is_gamma_correction_enabled()
+    assert not p.is_vignetting_correction_enabled() and p.is_undistortion_enabled()
+    assert not p.is_color_enhancer_enabled()  # flag is read from `run_color_enhancer` (App. B-4)
+    assert p._get_string("white_balance/method") == "ccc"
+    assert p._get_double("undistortion/fov_scale") == 0.8
+    # loadParams calls setHueGain three times (-> value_gain_ member = YAML value_gain)
+    assert p._get_double("color_enhancer/value_gain_member") == 1.0
+    assert p._get_double("color_enhancer/saturation_gain_member") == 1.0  # 1.5 in the YAML never lands
+    assert p.get_dist_image_width() == 720 and p.get_dist_image_height() == 540
+    assert p.get_dist_distortion_model() == "equidistant"
+    assert p.get_rect_distortion_model() == "none"  # undistortion enabled (undistortion.cpp:94-104)
+    np.testing.assert_allclose(p.get_color_calibration_matrix().ravel()[:3], [2.4276948, 0.21479778, -0.30818], rtol=1e-7)
+    assert p.get_color_calibration_bias().shape == (4, 1)
+    assert "Loading raw_image_pipeline params from file" in p.log()
+
+
+def test_four_argument_constructor_and_missing_files():
+    p = RawImagePipeline(False, "", "", "")  # empty calibration path: no camera calibration loaded
+    assert p.get_dist_distortion_model() == "none" and p.get_dist_image_width() == 0
+    q = RawImagePipeline(False, "/nonexistent/params.yaml", "/nonexistent/calib.yaml", "/nonexistent/color.yaml")
+    log = q.log()
+    assert "Warning: parameters file doesn't exist" in log
+    assert "Warning: Calibration file doesn't exist" in log
+    assert "Warning: Color calibration file doesn't exist" in log
+    assert q.get_dist_image_width() == 320 and q.get_dist_image_height() == 240  # undistortion.cpp:181
+    assert q.get_dist_distortion_model() == "none"
+
+
+def test_enhancer_setters_are_cross_wired_like_the_reference():
+    p = RawImagePipeline(False, "", "", "")
+    p.set_color_enhancer_hue_gain(1.1)         # -> value_gain_   (color_enhancer.cpp:23-25)
+    p.set_color_enhancer_saturation_gain(1.2)  # -> saturation_gain_
+    p.set_color_enhancer_value_gain(1.3)       # -> hue_gain_     (color_enhancer.cpp:31-33)
+    assert p._get_double("color_enhancer/value_gain_member") == 1.1
+    assert p._get_double("color_enhancer/saturation_gain_member") == 1.2
+    assert p._get_double("color_enhancer/hue_gain_member") == 1.3
+
+
+def test_setters_getters_roundtrip_and_errors():
+    p = RawImagePipeline(False, "", "", "")
+    for name in ("debayer", "flip", "white_balance", "color_calibration", "gamma_correction", "vignetting_correction",
+                 "color_enhancer", "undistortion"):
+        getattr(p, "set_" + name)(True)
+        assert getattr(p, "is_" + name + "_enabled")()
+        getattr(p, "set_" + name)(False)
+        assert not getattr(p, "is_" + name + "_enabled")()
+    p.set_flip_angle(270)
+    assert p._get_int("flip/angle") == 270
+    p.set_color_calibration_matrix([1, 2, 3, 4, 5, 6, 7, 8, 9.5])
+    assert p.get_color_calibration_matrix()[2, 2] == np.float32(9.5)
+    with pytest.raises(ValueError):
+        p.set_color_calibration_matrix([1, 2, 3])
+    with pytest.raises(RawImagePipelineError) as e:
+        p._set_bool("no/such/key", True)
+    assert e.value.code == L.RIP_ERR_UNKNOWN_KEY
+    # unknown white-balance method: std::invalid_argument with the reference's text (white_balance.hpp:81-85)
+    p.set_white_balance(True)
+    p.set_white_balance_method("magic")
+    with pytest.raises(ValueError, match=r"White Balance method \[magic\] not supported"):
+        p.process(np.zeros((8, 8), np.uint8), "bayer_rggb8")
+    p.set_white_balance_method("simple")
+    with pytest.raises(RawImagePipelineError) as e:
+        p.process(np.zeros((8, 8), np.uint8), "bayer_rggb8")
+    assert e.value.code == L.RIP_ERR_UNSUPPORTED
+    p.set_white_balance(False)
+    # 16-bit Bayer names listed by the reference throw (debayer.cpp:76-78, App. B-3)
+    with pytest.raises(ValueError, match="is a valid pattern but is not supported"):
+        p.process(np.zeros((8, 8), np.uint8), "bayer_rggb16")
+
+
+def test_output_shape_rules():
+    p = RawImagePipeline(False, "", "", "")
+    assert p.output_shape((480, 640), "bayer_rggb8") == (480, 640, 3)
+    p.set_flip(True); p.set_flip_angle(90)
+    assert p.output_shape((480, 640), "bayer_rggb8") == (640, 480, 3)
+    p.set_flip_angle(45)  # any other angle is a no-op even when enabled (flip.cpp:54-57)
+    assert p.output_shape((480, 640), "bayer_rggb8") == (480, 640, 3)
+    assert p.output_shape((480, 640, 3), "bgr8") == (480, 640, 3)
+
+
+@pytest.mark.parametrize("k", [0.8, 1.0, 0.45, 2.2, 1.3])
+def test_gamma_lut_matches_oracle(k):
+    p = RawImagePipeline(False, "", "", "")
+    p.set_gamma_correction_k(k)
+    lut = np.frombuffer(p.debug_table("gamma_lut"), np.uint8)
+    assert np.array_equal(lut, O.gamma_lut(k))
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (540, 720), (1080, 1920), (11, 13), (12, 10), (101, 64), (64, 101), (512, 512)])
+@pytest.mark.parametrize("par", [(1.5, 1e-3, 1e-6), (0.7, 2e-3, 0.0), (2.0, 0.0, 1e-7)])
+def test_vignetting_mask_matches_oracle(oracle_built, shape, par):
+    p = RawImagePipeline(False, "", "", "")
+    p.set_vignetting_correction_parameters(*par)
+    rows, cols = shape
+    mask = np.frombuffer(p.debug_table("vignetting_mask", rows, cols), np.float32).reshape(rows, cols)
+    ref = O.vignetting_mask(rows, cols, *par)
+    assert np.array_equal(mask.view(np.uint32), ref.view(np.uint32))
+
+
+def test_vignetting_mask_12mp_bit_exact(oracle_built):
+    p = RawImagePipeline(False, "", "", "")
+    mask = np.frombuffer(p.debug_table("vignetting_mask", 3040, 4032), np.float32).reshape(3040, 4032)
+    ref = O.vignetting_mask(3040, 4032, 1.5, 1e-3, 1e-6)
+    assert np.array_equal(mask.view(np.uint32), ref.view(np.uint32))
+
+
+def _setup_undistortion(p, calib, balance, fov, new_size=None):
+    p.set_undistortion_image_size(calib["width"], calib["height"])
+    if new_size:
+        p.set_undistortion_new_image_size(*new_size)
+    p.set_undistortion_camera_matrix(calib["K"])
+    p.set_undistortion_distortion_coeffs(calib["D"])
+    p.set_undistortion_distortion_model("equidistant")
+    p.set_undistortion_rectification_matrix([1, 0, 0, 0, 1, 0, 0, 0, 1])
+    p.set_undistortion_projection_matrix([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0])
+    p.set_undistortion_balance(balance)
+    p.set_undistortion_fov_scale(fov)
+
+
+@pytest.mark.parametrize("size", [(720, 540), (1920, 1080), (640, 480)])
+@pytest.mark.parametrize("balance,fov", [(0.0, 0.8), (0.5, 1.2), (1.0, 1.0)])
+def test_fisheye_new_camera_matrix_and_maps_match_cv2(size, balance, fov):
+    calib = scaled_calib(*size)
+    p = RawImagePipeline(False, "", "", "")
+    _setup_undistortion(p, calib, balance, fov)
+    newK, mx, my = O.undistortion_maps(calib["K"], calib["D"], np.eye(3).ravel(), size, size, balance, fov)
+    np.testing.assert_allclose(p.get_rect_camera_matrix(), newK, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(p.get_rect_projection_matrix()[:, :3], newK, rtol=0, atol=1e-9)
+    assert np.array_equal(p.get_rect_distortion_coefficients(), np.zeros((1, 4)))
+    m = np.frombuffer(p.debug_table("undistortion_map"), np.float32).reshape(size[1], size[0], 2)
+    # what matters to cv::remap is the 1/32-pixel quantised coordinate
+    assert int((np.rint(m[..., 0] * 32) != np.rint(mx * 32)).sum()) == 0
+    assert int((np.rint(m[..., 1] * 32) != np.rint(my * 32)).sum()) == 0
+    assert float(np.abs(m[..., 0] - mx).max()) <= 1e-3 and float(np.abs(m[..., 1] - my).max()) <= 1e-3
+
+
+def test_fisheye_new_size_and_1p6mp_calibration_file():
+    p = RawImagePipeline(False, "", os.path.join(CONFIG, "alphasense_calib_1.6mp_example.yaml"), "")
+    assert (p.get_dist_image_width(), p.get_dist_image_height()) == (1440, 1080)
+    p.set_undistortion_new_image_size(720, 540)
+    K = p.get_dist_camera_matrix(); D = p.get_dist_distortion_coefficients().reshape(4, 1)
+    ref = cv2.fisheye.estimateNewCameraMatrixForUndistortRectify(K, D, (1440, 1080), np.eye(3), balance=0.0,
+                                                                 new_size=(720, 540), fov_scale=0.8)  # default YAML
+    np.testing.assert_allclose(p.get_rect_camera_matrix(), ref, rtol=0, atol=1e-9)
+    assert (p.get_rect_image_width(), p.get_rect_image_height()) == (720, 540)
+
+
+def test_yaml_subset_parser_handles_reference_files(tmp_path):
+    y = tmp_path / "params.yaml"
+    y.write_text("# comment\nflip:\n  enabled: yes   # trailing\n  angle: 180\n"
+                 "gamma_correction: \n  enabled: True\n  method: 'custom'\n  k: 1.25\n"
+                 "color_enhancer:\n  run_color_enhancer: true\n  value_gain: 1.4\n"
+                 "undistortion:\n  enabled: false\n")
+    p = RawImagePipeline(False, str(y), "", "")
+    assert p.is_flip_enabled() and p._get_int("flip/angle") == 180
+    assert p.is_gamma_correction_enabled() and p._get_double("gamma_correction/k") == 1.25
+    assert p.is_color_enhancer_enabled() and p._get_double("color_enhancer/value_gain_member") == 1.4
+    assert not p.is_undistortion_enabled() and not p.is_white_balance_enabled()  # defaults of cpp:77,148
+    c = tmp_path / "color.yaml"
+    c.write_text("matrix:\n  rows: 3\n  cols: 3\n  data: [1.5, 0, 0,\n         0, 1.25, 0,\n         0, 0, 2]\nbias:\n  data: [1, 2, 3]\n")
+    p.load_color_calibration(str(c))
+    assert np.array_equal(p.get_color_calibration_matrix(), np.diag([1.5, 1.25, 2]).astype(np.float32))
+    assert np.array_equal(p.get_color_calibration_bias().ravel(), [1, 2, 3, 0])
