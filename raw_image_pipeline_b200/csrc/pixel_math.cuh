@@ -152,8 +152,12 @@ RIP_HD void bgr_to_hsv(int b, int g, int r, const ChainTables& t, int& h, int& s
   v = vmax;
 }
 
-// ---- 8-bit HSV -> BGR: color_enhancer.cpp:46 (A.9; fp32 with FMA, truncation) -----------
-RIP_HD void hsv_to_bgr(int h, int s, int v, int& b, int& g, int& r) {
+// ---- 8-bit HSV -> BGR: color_enhancer.cpp:46 (A.9; fp32 with FMA) ------------------------
+// OpenCV's HSV2RGB_b converts each image row in vector chunks of 32 pixels (AVX2 dispatch: 4 x 8
+// lanes) whose results are TRUNCATED to u8, and finishes the remaining (width % 32) pixels of
+// the row with scalar code that ROUNDS (saturate_cast) [probed exhaustively, cv2 4.13.0: both
+// paths use the fused form 1 - s*f].  `row_tail` = this pixel's column >= (width & ~31).
+RIP_HD void hsv_to_bgr(int h, int s, int v, bool row_tail, int& b, int& g, int& r) {
   float hh = RIP_FMUL((float)h, 6.0f / 180.0f);
   if (hh >= 6.0f) hh = RIP_FSUB(hh, 6.0f);
   const float secf = RIP_FLOORF(hh);
@@ -176,9 +180,12 @@ RIP_HD void hsv_to_bgr(int h, int s, int v, int& b, int& g, int& r) {
     case 4: fb = t0; fg = t1; fr = t3; break;
     default: fb = t2; fg = t1; fr = t0; break;
   }
-  b = RIP_TRUNC_I(RIP_FMUL(fb, 255.0f)) & 255;
-  g = RIP_TRUNC_I(RIP_FMUL(fg, 255.0f)) & 255;
-  r = RIP_TRUNC_I(RIP_FMUL(fr, 255.0f)) & 255;
+  fb = RIP_FMUL(fb, 255.0f); fg = RIP_FMUL(fg, 255.0f); fr = RIP_FMUL(fr, 255.0f);
+  if (row_tail) {
+    b = sat_u8_rint(fb); g = sat_u8_rint(fg); r = sat_u8_rint(fr);
+  } else {
+    b = RIP_TRUNC_I(fb) & 255; g = RIP_TRUNC_I(fg) & 255; r = RIP_TRUNC_I(fr) & 255;
+  }
 }
 
 // ---- enhancer: color_enhancer.cpp:38-47 -------------------------------------------------
@@ -200,16 +207,16 @@ RIP_HD int enh_gain_lut_entry(int x, double gain) {
 #endif
 }
 
-RIP_HD void enhance(int& b, int& g, int& r, const ChainTables& t) {
+RIP_HD void enhance(int& b, int& g, int& r, bool row_tail, const ChainTables& t) {
   int h, s, v;
   bgr_to_hsv(b, g, r, t, h, s, v);
   h = t.enh[h]; s = t.enh[256 + s]; v = t.enh[512 + v];
-  hsv_to_bgr(h, s, v, b, g, r);
+  hsv_to_bgr(h, s, v, row_tail, b, g, r);
 }
 
 // ---- the chain after debayer+flip: raw_image_pipeline.hpp:151-166 -----------------------
 template <uint32_t STAGES>
-RIP_HD void chain_pixel(int& b, int& g, int& r, float mask, const ChainConsts& k, const ChainTables& t) {
+RIP_HD void chain_pixel(int& b, int& g, int& r, float mask, bool row_tail, const ChainConsts& k, const ChainTables& t) {
   if (STAGES & ST_WB) {  // white_balance.cpp:117-127 (pca) / ccc.cpp:383-386: per-frame LUTs
     b = t.wb[b]; g = t.wb[256 + g]; r = t.wb[512 + r];
   }
@@ -218,7 +225,7 @@ RIP_HD void chain_pixel(int& b, int& g, int& r, float mask, const ChainConsts& k
     b = t.gamma[b]; g = t.gamma[g]; r = t.gamma[r];
   }
   if (STAGES & ST_VIG) vignetting(b, g, r, mask, t);
-  if (STAGES & ST_ENH) enhance(b, g, r, t);
+  if (STAGES & ST_ENH) enhance(b, g, r, row_tail, t);
 }
 
 // ---- cv::remap INTER_LINEAR fixed point: undistortion.cpp:240-245 (A.10) ----------------

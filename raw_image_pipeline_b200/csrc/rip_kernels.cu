@@ -208,13 +208,17 @@ __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ Fram
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float m = 1.0f;
-        if (STAGES & ST_VIG) {
+        bool row_tail = false;
+        if (STAGES & (ST_VIG | ST_ENH)) {  // stages that depend on the post-flip pixel position
           int oy, ox;
           flip_dest(P.angle, P.rows, P.cols, y, min(x + k, P.cols - 1), oy, ox);
-          const int qi = abs(2 * oy - P.orows) >> 1, qj = abs(2 * ox - P.ocols) >> 1;
-          m = __ldg(P.vig + (size_t)qi * P.vig_pitch + qj);
+          if (STAGES & ST_VIG) {
+            const int qi = abs(2 * oy - P.orows) >> 1, qj = abs(2 * ox - P.ocols) >> 1;
+            m = __ldg(P.vig + (size_t)qi * P.vig_pitch + qj);
+          }
+          row_tail = ox >= (P.ocols & ~31);  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
         }
-        chain_pixel<STAGES>(b[k], g[k], r[k], m, P.k, T);
+        chain_pixel<STAGES>(b[k], g[k], r[k], m, row_tail, P.k, T);
       }
       if (staged_out) {
         if (P.angle == 0) {

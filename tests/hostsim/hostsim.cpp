@@ -39,15 +39,17 @@ void hs_bgr2hsv(long n, const uint8_t* in, uint8_t* out) {
     out[3 * i] = h; out[3 * i + 1] = s; out[3 * i + 2] = v;
   }
 }
-void hs_hsv2bgr(long n, const uint8_t* in, uint8_t* out) {
+// `width`: row length of the image the n pixels form (selects OpenCV's scalar row tail)
+void hs_hsv2bgr(long n, int width, const uint8_t* in, uint8_t* out) {
   for (long i = 0; i < n; ++i) {
-    int b, g, r; hsv_to_bgr(in[3 * i], in[3 * i + 1], in[3 * i + 2], b, g, r);
+    const bool tail = (int)(i % width) >= (width & ~31);
+    int b, g, r; hsv_to_bgr(in[3 * i], in[3 * i + 1], in[3 * i + 2], tail, b, g, r);
     out[3 * i] = b; out[3 * i + 1] = g; out[3 * i + 2] = r;
   }
 }
 
 // full per-pixel chain; mask may be null when ST_VIG is off
-void hs_chain(unsigned stages, long n, const uint8_t* in, const float* mask, const float* cc, const float* bias,
+void hs_chain(unsigned stages, long n, int width, const uint8_t* in, const float* mask, const float* cc, const float* bias,
               const double* enh, const uint8_t* wb, const uint8_t* gamma, uint8_t* out) {
   ChainTables t = make_tables(wb, gamma);
   ChainConsts k;
@@ -63,7 +65,7 @@ void hs_chain(unsigned stages, long n, const uint8_t* in, const float* mask, con
     if (stages & ST_CC) color_calibrate(b, g, r, k);
     if (stages & ST_GAMMA) { b = t.gamma[b]; g = t.gamma[g]; r = t.gamma[r]; }
     if (stages & ST_VIG) vignetting(b, g, r, m, t);
-    if (stages & ST_ENH) enhance(b, g, r, t);
+    if (stages & ST_ENH) enhance(b, g, r, (int)(i % width) >= (width & ~31), t);
     out[3 * i] = b; out[3 * i + 1] = g; out[3 * i + 2] = r;
   }
 }

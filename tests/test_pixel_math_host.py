@@ -12,9 +12,12 @@ from oracle import cv2_oracle as O
 P = ctypes.c_void_p
 
 
-def _run3(fn, img):
+def _run3(fn, img, with_width=False):
     out = np.empty_like(img)
-    fn(ctypes.c_long(img.shape[0] * img.shape[1]), P(img.ctypes.data), P(out.ctypes.data))
+    if with_width:
+        fn(ctypes.c_long(img.shape[0] * img.shape[1]), ctypes.c_int(img.shape[1]), P(img.ctypes.data), P(out.ctypes.data))
+    else:
+        fn(ctypes.c_long(img.shape[0] * img.shape[1]), P(img.ctypes.data), P(out.ctypes.data))
     return out
 
 
@@ -22,7 +25,21 @@ def _run3(fn, img):
                                        ("hs_bgr2hsv", cv2.COLOR_BGR2HSV), ("hs_hsv2bgr", cv2.COLOR_HSV2BGR)])
 def test_colour_conversions_exhaustive(hostsim, name, code):
     img = cube()
-    got = _run3(getattr(hostsim, name), img)
+    got = _run3(getattr(hostsim, name), img, with_width=(name == "hs_hsv2bgr"))
+    ref = cv2.cvtColor(img, code)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("width", [31, 45, 100])
+@pytest.mark.parametrize("name,code", [("hs_bgr2lab", cv2.COLOR_BGR2Lab), ("hs_lab2bgr", cv2.COLOR_Lab2BGR),
+                                       ("hs_bgr2hsv", cv2.COLOR_BGR2HSV), ("hs_hsv2bgr", cv2.COLOR_HSV2BGR)])
+def test_colour_conversions_exhaustive_in_row_tails(hostsim, name, code, width):
+    """cv2 finishes each row's last (width % 32) pixels with scalar code; HSV2BGR rounds there
+    instead of truncating.  All 2^24 triples again, laid out so that they land in row tails."""
+    flat = cube().reshape(-1, 3)
+    pad = (-len(flat)) % width
+    img = np.ascontiguousarray(np.concatenate([flat, flat[:pad]]).reshape(-1, width, 3))
+    got = _run3(getattr(hostsim, name), img, with_width=(name == "hs_hsv2bgr"))
     ref = cv2.cvtColor(img, code)
     assert int((got != ref).sum()) == 0
 
@@ -36,7 +53,7 @@ def _chain(hostsim, stages, img, mask=None, cc=None, bias=(0, 0, 0), enh=(1, 1, 
     gamma = np.ascontiguousarray(gamma if gamma is not None else np.arange(256, dtype=np.uint8))
     out = np.empty_like(img)
     m = None if mask is None else np.ascontiguousarray(mask, np.float32)
-    hostsim.hs_chain(ctypes.c_uint(stages), ctypes.c_long(n), P(img.ctypes.data),
+    hostsim.hs_chain(ctypes.c_uint(stages), ctypes.c_long(n), ctypes.c_int(img.shape[1]), P(img.ctypes.data),
                      P(m.ctypes.data) if m is not None else None, P(cc.ctypes.data), P(bias.ctypes.data),
                      P(enh.ctypes.data), P(wb.ctypes.data), P(gamma.ctypes.data), P(out.ctypes.data))
     return out
@@ -81,9 +98,9 @@ def test_vignetting_L_times_mask_dense(hostsim):
     assert int((got != ref).sum()) == 0
 
 
-def test_gamma_and_full_chain_random(hostsim, oracle_built):
+@pytest.mark.parametrize("rows,cols", [(480, 640), (270, 362), (33, 17)])
+def test_gamma_and_full_chain_random(hostsim, oracle_built, rows, cols):
     rng = np.random.default_rng(11)
-    rows, cols = 480, 640
     img = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
     mask = O.vignetting_mask(rows, cols, 1.5, 1e-3, 1e-6)
     glut = O.gamma_lut(0.8)
