@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -78,49 +77,58 @@ def make_frames(n, rows, cols, seed0, distinct=16):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event reasons sampled through NVML (in-process thread, every ~5 ms)
+    DURING the timed region."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self.stop_flag, self.thread, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = nv
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        reasons = set()
+        for _, r, _ in self.samples:
+            for bit, name in names.items():
+                if r & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max((s[2] for s in self.samples), default=None)}
 
 
 def hbm_peak():
@@ -241,18 +249,21 @@ def run_b200(args):
     def step_host():
         p.process_batch_ptr(h_in.data_ptr(), n, rows, cols, 1, ENC, h_out.data_ptr(), host=True)
 
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    torch.cuda.synchronize()
-    dt_e2e = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e = world * n * rows * cols * args.steps / dt_e2e / 1e6
-    # parity spot check of the timed outputs: device batch == host batch for frame 0
-    same = bool(torch.equal(d_out[0].cpu(), h_out[0]))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
+    e2e, dt_e2e, same = None, 0.0, None
+    if e2e_steps:
+        for _ in range(min(args.warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt_e2e = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = world * n * rows * cols * e2e_steps / dt_e2e / 1e6
+        # parity spot check of the timed outputs: device batch == host batch for frame 0
+        same = bool(torch.equal(d_out[0].cpu(), h_out[0]))
 
     if rank != 0:
         if world > 1:
@@ -284,7 +295,9 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fused_ms,
                      "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)"},
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * rows * cols) * world,
-                "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "ms_per_step": dt_e2e / args.steps * 1e3},
+                "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "steps": e2e_steps,
+                "ms_per_step": dt_e2e / max(e2e_steps, 1) * 1e3,
+                "api": "rip_apply_batch_host (pinned host buffers, H2D + kernels + D2H inside the timed region, host wall clock)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -302,13 +315,15 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU (BASELINE configs[2]: 64)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames timed for cpu_baseline")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -424,7 +424,7 @@ int rip_load_camera_calibration(rip_pipeline* p, const char* path) { p->hs.load_
 int rip_load_color_calibration(rip_pipeline* p, const char* path) { p->hs.load_color_calibration(path ? path : ""); return RIP_OK; }
 int rip_init_undistortion(rip_pipeline* p) { p->hs.init_undistortion(); return RIP_OK; }
 int rip_reset_white_balance_temporal_consistency(rip_pipeline* p) {
-  if (p->hs.p.wb_method == "ccc") p->ccc.first_frame = true;  // white_balance.cpp:42-47
+  if (p->hs.p.wb_method == "ccc") p->ccc.pending_reset = true;  // white_balance.cpp:42-47 -> first_frame_ = true
   return RIP_OK;
 }
 
@@ -620,6 +620,14 @@ int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void*
     build_host_map(p);
     data.resize(p->h_map.size() * 4);
     memcpy(data.data(), p->h_map.data(), data.size());
+  } else if (key_is(name, "ccc_response")) {  // last frame of the last call: 256 x 256 fp64, == cv2 response / 65536 - bias
+    if (!p->ccc.d_last_response) return p->fail(RIP_ERR_INVALID_ARGUMENT, "no CCC frame processed yet");
+    std::vector<double> cplx(2 * 65536);
+    RIP_CUDA(p, cudaDeviceSynchronize());
+    RIP_CUDA(p, cudaMemcpy(cplx.data(), p->ccc.d_last_response, cplx.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    data.resize(65536 * sizeof(double));
+    double* o = reinterpret_cast<double*>(data.data());
+    for (int i = 0; i < 65536; ++i) o[i] = cplx[2 * i] * (1.0 / 65536.0);
   } else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown table: ") + name);
   if (bytes) *bytes = data.size();
   if (!out || capacity < data.size()) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "table buffer too small");
@@ -661,6 +669,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   if (rc != RIP_OK) return rc;
   RIP_CUDA(p, cudaMemcpyAsync(out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
   if (wbk == 1) RIP_CUDA(p, cudaMemcpyAsync(p->last_pca, p->scratch.coeff.ptr, sizeof p->last_pca, cudaMemcpyDeviceToHost, p->stream));
+  if (wbk == 2 && (rc = ccc_fetch_last(p->ccc, p->scratch.gains, p->stream, p->last_error)) != RIP_OK) return rc;
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
   p->have_frame = true; p->last_geom = g; p->last_in_encoding = encoding;
   memcpy(encoding, g.out_encoding.c_str(), g.out_encoding.size() + 1);

@@ -3,7 +3,7 @@
 // exhaustively with cv2 before the CUDA build ever meets a GPU.  Never linked into, loaded
 // by, or shipped with the product library (raw_image_pipeline_b200/librip_b200.so).
 #include <cstring>
-#include "../../raw_image_pipeline_b200/csrc/frame_math.cuh"
+#include "../../raw_image_pipeline_b200/csrc/ccc_math.cuh"
 #include "../../raw_image_pipeline_b200/csrc/cv_tables.inc"
 
 using namespace rip;
@@ -119,5 +119,41 @@ void hs_pca_lut(const unsigned long long* stats, uint8_t* lut_b, uint8_t* lut_r,
 void hs_gain_lut(float gain, uint8_t* lut) {
   for (int x = 0; x < 256; ++x) lut[x] = gain_lut_entry(x, gain);
 }
+
+// ---- CCC white balance pieces (ccc_math.cuh) ---------------------------------------------------
+// cv::resize(img, 360x270, INTER_LINEAR) of a rows x cols BGR8 image
+void hs_ccc_small(const uint8_t* img, int rows, int cols, uint8_t* out) {
+  for (int dy = 0; dy < CCC_SMALL_H; ++dy) {
+    const CccAxisCoef cy = ccc_axis_coef(rows, CCC_SMALL_H, dy);
+    const int y0 = cy.s < 0 ? 0 : (cy.s > rows - 1 ? rows - 1 : cy.s);
+    const int y1 = cy.s + 1 < 0 ? 0 : (cy.s + 1 > rows - 1 ? rows - 1 : cy.s + 1);
+    for (int dx = 0; dx < CCC_SMALL_W; ++dx) {
+      const CccAxisCoef cx = ccc_axis_coef_horizontal(cols, CCC_SMALL_W, dx);
+      const int x0 = cx.s, x1 = cx.s + 1 > cols - 1 ? cols - 1 : cx.s + 1;
+      for (int c = 0; c < 3; ++c) {
+        const int S0 = ccc_hresize(img[((size_t)y0 * cols + x0) * 3 + c], img[((size_t)y0 * cols + x1) * 3 + c], cx.a0, cx.a1);
+        const int S1 = ccc_hresize(img[((size_t)y1 * cols + x0) * 3 + c], img[((size_t)y1 * cols + x1) * 3 + c], cx.a0, cx.a1);
+        out[((size_t)dy * CCC_SMALL_W + dx) * 3 + c] = (uint8_t)ccc_vresize(S0, S1, cy.a0, cy.a1);
+      }
+    }
+  }
+}
+
+// histogram counts of the small image; returns the number of samples that landed in a bin
+long hs_ccc_counts(const uint8_t* small_bgr, long n, float thr_hi, float thr_lo, float uv0, float bin_size, unsigned* counts) {
+  float log_tab[256];
+  memcpy(log_tab, kCvLogTabBits, sizeof log_tab);
+  long used = 0;
+  for (long i = 0; i < n; ++i) {
+    int u, v;
+    if (ccc_bin(small_bgr[3 * i], small_bgr[3 * i + 1], small_bgr[3 * i + 2], thr_hi, thr_lo, log_tab, uv0, bin_size, u, v)) {
+      counts[u * CCC_BINS + v] += 1;
+      ++used;
+    }
+  }
+  return used;
+}
+
+void hs_ccc_gains(int uv_x, int uv_y, const float* exp_tab, float* gains_bgr) { ccc_gains(uv_x, uv_y, exp_tab, gains_bgr); }
 
 }  // extern "C"

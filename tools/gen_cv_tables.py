@@ -139,6 +139,31 @@ def main():
         f.write(arr("unsigned char", "kSrgbInvGammaTab", IG, 32))
         f.write(arr("int", "kHsvSdiv", SDIV, 8))
         f.write(arr("int", "kHsvHdiv", HDIV, 8))
+        # cv::log on CV_32F (core mathfuncs, table + polynomial, not libm) for the 256 values an 8-bit
+        # channel can take, as IEEE-754 bit patterns; entry 0 is -inf.  Position-independent [checked below].
+        x = np.arange(256, dtype=np.float32)
+        with np.errstate(all="ignore"):
+            lg = cv2.log(x.reshape(1, -1)).ravel()
+            for n, off in ((1, 5), (7, 100), (33, 200), (256, 0)):
+                assert np.array_equal(cv2.log(np.ascontiguousarray(x[off:off + n]).reshape(1, -1)).ravel(), lg[off:off + n])
+        f.write("// cv::log(float(i)), i = 0..255, as raw IEEE-754 bits (reinterpret as float)\n")
+        f.write(arr("unsigned int", "kCvLogTabBits", lg.view(np.uint32), 8))
+        # cv::KalmanFilter(2, 2, 0, CV_32F) with A = H = Q = I, R = 10 I, P0 = 0 (ccc.cpp:176-203): the gain
+        # is data-independent, stays a multiple of I and reaches its fp32 fixed point after < 40 steps.
+        # Tabulated from cv2 because correct() solves through an fp32 SVD whose rounding has no closed form.
+        kf = cv2.KalmanFilter(2, 2, 0, cv2.CV_32F)
+        kf.transitionMatrix = np.eye(2, dtype=np.float32); kf.processNoiseCov = np.eye(2, dtype=np.float32)
+        kf.measurementMatrix = np.eye(2, dtype=np.float32); kf.measurementNoiseCov = 10 * np.eye(2, dtype=np.float32)
+        gains = []
+        for k in range(64):
+            kf.predict(); kf.correct(np.array([[k % 7], [3 * k % 11]], np.float32))
+            g = kf.gain
+            assert g[0, 1] == 0 and g[1, 0] == 0 and g[0, 0] == g[1, 1]
+            gains.append(g[0, 0])
+        gains = np.array(gains, np.float32)
+        assert np.all(gains[40:] == gains[40])
+        f.write("// gain of the k-th cv::KalmanFilter::correct() call of the CCC tracker (fixed point from entry 39 on)\n")
+        f.write(arr("unsigned int", "kCccKalmanGainBits", gains[:40].view(np.uint32), 8))
     print("wrote", os.path.normpath(OUT))
 
 
