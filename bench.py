@@ -203,12 +203,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from raw_image_pipeline_b200 import sharding
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device=dev)
 
     n, rows, cols = args.frames, ROWS, COLS
     p = make_pipeline(rows, cols, device=local)
