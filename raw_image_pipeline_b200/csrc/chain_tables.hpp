@@ -1,0 +1,112 @@
+// Host-side construction of the static lookup-table blob the fused kernel copies into shared
+// memory (layout below), from OpenCV's colour-conversion constants (cv_tables.inc) and the
+// pipeline parameters.  Plain C++ (no CUDA types): shared by the library (rip_api.cu) and the
+// CPU-only test harness (tests/hostsim).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "cv_tables.inc"
+#include "pixel_math.cuh"
+
+namespace rip {
+
+// byte offsets inside the blob
+enum : int {
+  OFF_GAMMA = 0,      // u8[256]       gamma LUT (identity if gamma is off)     gamma_correction.cpp:35-42
+  OFF_INVG = 256,     // u8[4096]      sRGBInvGammaTab_b
+  OFF_G2 = 4352,      // u16[256]      sRGBGammaTab_b[gamma[x]]
+  OFF_LABC = 4864,    // u16[2048]     LabCbrtTab_b (2041 used)
+  OFF_YF = 8960,      // u32[256]      LabToYF_b packed (ify << 16) | y
+  OFF_SDIV = 9984,    // i32[256]
+  OFF_HDIV = 11008,   // i32[256]
+  OFF_HUE = 12032,    // HueEntry[256] enhancer hue gain + HSV2BGR sector/fraction
+  OFF_SF = 14080,     // f32[256]      enhancer saturation gain, * 1/255f
+  OFF_VF = 15104,     // f32[256]      enhancer value gain, * 1/255f
+  TABLE_BYTES = 16128
+};
+
+struct ChainTableParams {
+  bool gamma_enabled = false;
+  double gamma_k = 1.0;
+  double enh_gain[3] = {1.0, 1.0, 1.0};  // (hue_gain_, saturation_gain_, value_gain_) member values
+  bool operator==(const ChainTableParams& o) const {
+    return gamma_enabled == o.gamma_enabled && gamma_k == o.gamma_k && memcmp(enh_gain, o.enh_gain, sizeof enh_gain) == 0;
+  }
+};
+
+// gamma_correction.cpp:38-41:  float f = i / 255.0; f = pow(f, k_); lut = saturate_cast<uchar>(f * 255.0);
+inline void build_gamma_lut(double k, uint8_t lut[256]) {
+  for (int i = 0; i < 256; ++i) {
+    float f = (float)(i / 255.0);
+    f = (float)pow((double)f, k);
+    const double v = (double)f * 255.0;
+    int iv;
+    if (!(v == v)) iv = 0;
+    else if (v <= -1.0) iv = 0;
+    else if (v >= 256.0) iv = 255;
+    else iv = (int)lrint(v);
+    lut[i] = (uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+  }
+}
+
+// PRMT selector for HSV2RGB_b's sector table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} (b, g, r -> index
+// into (t0, t1, t2, t3)); byte 3 of the result is don't-care.
+inline uint32_t hsv_sector_selector(int sector) {
+  static const uint32_t k[6] = {0x4031, 0x4201, 0x4103, 0x4120, 0x4310, 0x4012};  // b | g << 4 | r << 8 | (zero byte) << 12
+  return k[sector < 0 ? 0 : (sector > 5 ? 5 : sector)];
+}
+
+inline void build_chain_blob(const ChainTableParams& q, uint8_t* blob) {
+  memset(blob, 0, TABLE_BYTES);
+  uint8_t* gamma = blob + OFF_GAMMA;
+  if (q.gamma_enabled) build_gamma_lut(q.gamma_k, gamma);
+  else for (int i = 0; i < 256; ++i) gamma[i] = (uint8_t)i;
+  memcpy(blob + OFF_INVG, kSrgbInvGammaTab, sizeof kSrgbInvGammaTab);
+  uint16_t* g2 = reinterpret_cast<uint16_t*>(blob + OFF_G2);
+  for (int i = 0; i < 256; ++i) g2[i] = kSrgbGammaTab[gamma[i]];
+  memcpy(blob + OFF_LABC, kLabCbrtTab, sizeof kLabCbrtTab);
+  memcpy(blob + OFF_YF, kLabToYF, sizeof kLabToYF);
+  memcpy(blob + OFF_SDIV, kHsvSdiv, sizeof kHsvSdiv);
+  memcpy(blob + OFF_HDIV, kHsvHdiv, sizeof kHsvHdiv);
+  HueEntry* hue = reinterpret_cast<HueEntry*>(blob + OFF_HUE);
+  float* sf = reinterpret_cast<float*>(blob + OFF_SF);
+  float* vf = reinterpret_cast<float*>(blob + OFF_VF);
+  for (int i = 0; i < 256; ++i) {
+    // color_enhancer.cpp:42 cv::multiply(hsv, Scalar(hue_gain_, saturation_gain_, value_gain_))
+    const int h = enh_gain_lut_entry(i, q.enh_gain[0]), s = enh_gain_lut_entry(i, q.enh_gain[1]), v = enh_gain_lut_entry(i, q.enh_gain[2]);
+    // HSV2RGB_b: h * (6/180f), wrap, sector, fraction (fp32, each operation rounded on its own)
+    volatile float hh = (float)h * (6.0f / 180.0f);
+    if (hh >= 6.0f) hh = hh - 6.0f;
+    const float secf = floorf(hh);
+    volatile float f = hh - secf;
+    hue[i].f = f;
+    hue[i].sel = hsv_sector_selector((int)secf);
+    volatile float s1 = (float)s * (1.0f / 255.0f), v1 = (float)v * (1.0f / 255.0f);
+    sf[i] = s1; vf[i] = v1;
+  }
+}
+
+// pointers into a blob (host memory or shared memory); wbf is set by the caller
+inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+ChainTables chain_tables_from_blob(const uint8_t* t, const float* wbf) {
+  ChainTables c;
+  c.wbf = wbf;
+  c.gamma = t + OFF_GAMMA;
+  c.inv_g = t + OFF_INVG;
+  c.g2 = reinterpret_cast<const uint16_t*>(t + OFF_G2);
+  c.lab_c = reinterpret_cast<const uint16_t*>(t + OFF_LABC);
+  c.lab_yf = reinterpret_cast<const uint32_t*>(t + OFF_YF);
+  c.sdiv = reinterpret_cast<const int32_t*>(t + OFF_SDIV);
+  c.hdiv = reinterpret_cast<const int32_t*>(t + OFF_HDIV);
+  c.hue = reinterpret_cast<const HueEntry*>(t + OFF_HUE);
+  c.sf = reinterpret_cast<const float*>(t + OFF_SF);
+  c.vf = reinterpret_cast<const float*>(t + OFF_VF);
+  return c;
+}
+
+}  // namespace rip

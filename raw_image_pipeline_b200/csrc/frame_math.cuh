@@ -70,6 +70,42 @@ RIP_HD void demosaic_quad(const uint32_t w[3][3], bool row_has_r, int cpar, int 
   }
 }
 
+// ---- the same four sites with packed-byte (SWAR) arithmetic: the kernels' fast path -------------
+// Inputs as for demosaic_quad (three rows of three words).  Outputs are packed words whose byte k is the
+// B / G / R value of column x + k.  ~45 integer operations per quad instead of ~100.
+RIP_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int shift) {  // low 32 bits of ((hi:lo) >> shift), 0 < shift < 32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, shift);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> shift);
+#endif
+}
+// per-byte (a + b + 1) >> 1
+RIP_HD uint32_t avg_round_u8x4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1); }
+// bytes (p, p + 2) of w as two 16-bit lanes
+RIP_HD uint32_t lanes16(uint32_t w, int p) { return prmt(w, 0u, p ? 0x4341u : 0x4240u); }
+
+RIP_HD void demosaic_quad_swar(const uint32_t w[3][3], bool row_has_r, int cpar, uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const uint32_t Nc = w[0][1], Mc = w[1][1], Sc = w[2][1];
+  const uint32_t Nl = funnel_r(w[0][0], Nc, 24), Nr = funnel_r(Nc, w[0][2], 8);  // columns x-1..x+2 / x+1..x+4
+  const uint32_t Ml = funnel_r(w[1][0], Mc, 24), Mr = funnel_r(Mc, w[1][2], 8);
+  const uint32_t Sl = funnel_r(w[2][0], Sc, 24), Sr = funnel_r(Sc, w[2][2], 8);
+  const uint32_t H = avg_round_u8x4(Ml, Mr);  // (W + E + 1) >> 1 at every column
+  const uint32_t V = avg_round_u8x4(Nc, Sc);  // (N + S + 1) >> 1
+  // colour sites (column parity cpar): 4-neighbour sums in 16-bit lanes
+  const uint32_t X = ((lanes16(Nc, cpar) + lanes16(Sc, cpar) + lanes16(Ml, cpar) + lanes16(Mr, cpar) + 0x00020002u) >> 2) & 0x00ff00ffu;
+  const uint32_t D = ((lanes16(Nl, cpar) + lanes16(Nr, cpar) + lanes16(Sl, cpar) + lanes16(Sr, cpar) + 0x00020002u) >> 2) & 0x00ff00ffu;
+  // merge: at colour sites G = cross, native = raw, opposite = diagonal; at green sites G = raw,
+  // the row's colour = horizontal average, the other colour = vertical average
+  const uint32_t sel = cpar ? 0x2604u : 0x7250u;            // lane values at the colour sites, second operand elsewhere
+  const uint32_t site = cpar ? 0xff00ff00u : 0x00ff00ffu;  // byte mask of the colour sites
+  Gw = prmt(X, Mc, sel);
+  const uint32_t row_colour = (Mc & site) | (H & ~site);
+  const uint32_t other_colour = prmt(D, V, sel);
+  Rw = row_has_r ? row_colour : other_colour;
+  Bw = row_has_r ? other_colour : row_colour;
+}
+
 // ---- flip.cpp:37-58 as an index map: source coordinate of output pixel (oy, ox) ----------
 // angle 90: out(y,x)=in(H-1-x, y); 180: in(H-1-y, W-1-x); 270: in(x, W-1-y)   
 RIP_HD void flip_source(int angle, int rows, int cols, int oy, int ox, int& iy, int& ix) {

@@ -10,7 +10,7 @@
 #include <sstream>
 #include <thread>
 
-#include "pixel_math.cuh"
+#include "chain_tables.hpp"
 
 namespace rip {
 
@@ -151,21 +151,6 @@ std::vector<double> YamlDoc::get_doubles(const std::string& k) const {
 // ---------------------------------------------------------------------------------------------
 // host tables
 // ---------------------------------------------------------------------------------------------
-void build_gamma_lut(double k, uint8_t lut[256]) {
-  // gamma_correction.cpp:38-41:  float f = i / 255.0; f = pow(f, k_); lut = saturate_cast<uchar>(f * 255.0);
-  for (int i = 0; i < 256; ++i) {
-    float f = (float)(i / 255.0);
-    f = (float)std::pow((double)f, k);
-    const double v = (double)f * 255.0;
-    int iv;
-    if (!(v == v)) iv = 0;
-    else if (v <= -1.0) iv = 0;
-    else if (v >= 256.0) iv = 255;
-    else iv = (int)std::lrint(v);
-    lut[i] = (uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
-  }
-}
-
 void build_enhancer_luts(const Params& p, uint8_t lut[768]) {
   const double g[3] = {p.enh_hue_gain, p.enh_saturation_gain, p.enh_value_gain};
   for (int c = 0; c < 3; ++c)

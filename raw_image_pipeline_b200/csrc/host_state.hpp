@@ -69,7 +69,7 @@ struct Params {
 };
 
 // Host-computed tables.
-void build_gamma_lut(double k, uint8_t lut[256]);                        // gamma_correction.cpp:35-42
+// build_gamma_lut (gamma_correction.cpp:35-42) lives in chain_tables.hpp
 void build_enhancer_luts(const Params& p, uint8_t lut[768]);             // color_enhancer.cpp:42
 // vignetting_correction.cpp:32-63 for a rows x cols image, stored as the (rows/2+1) x (cols/2+1)
 // quadrant indexed by (|2i - rows| >> 1, |2j - cols| >> 1): the mask depends only on |i - rows/2|

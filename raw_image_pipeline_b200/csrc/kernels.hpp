@@ -4,22 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "pixel_math.cuh"
+#include "chain_tables.hpp"
 
 namespace rip {
-
-// byte offsets inside the static table blob (device global, copied to shared memory per CTA)
-enum : int {
-  OFF_GAMMA = 0,      // u8[256]    gamma LUT                       gamma_correction.cpp:35-42
-  OFF_ENH = 256,      // u8[3][256] enhancer H,S,V gain LUTs        color_enhancer.cpp:42
-  OFF_INVG = 1024,    // u8[4096]   sRGBInvGammaTab_b
-  OFF_SRGBG = 5120,   // u16[256]   sRGBGammaTab_b
-  OFF_LABC = 5632,    // u16[2048]  LabCbrtTab_b (2041 used)
-  OFF_YF = 9728,      // u32[256]   LabToYF_b packed (ify << 16) | y
-  OFF_SDIV = 10752,   // i32[256]
-  OFF_HDIV = 11776,   // i32[256]
-  TABLE_BYTES = 12800
-};
 
 enum : int { SRC_BAYER = 0, SRC_BGR = 1, SRC_RGB = 2 };
 
@@ -36,9 +23,9 @@ struct FrameParams {
   int angle;                  // 0 / 90 / 180 / 270
   int src;                    // SRC_*
   const uint8_t* tables;      // static blob (TABLE_BYTES)
-  const uint8_t* wb;          // n_frames x 768 per-frame white-balance LUTs (B,G,R) or null
-  const float* vig;           // vignetting quadrant or null
-  int vig_pitch;              // floats per quadrant row
+  const float* wbf;           // n_frames x 3 x 256 per-frame white-balance LUTs (B,G,R) as floats, or null
+  const float* vig;           // vignetting mask, upper half: (orows/2 + 1) x ocols, row qi = |2*oy - orows| >> 1
+  int vig_pitch;              // floats per mask row (== ocols)
   ChainConsts k;
   unsigned long long* stats;  // n_frames x 8 (stats kernel only)
 };
@@ -57,9 +44,15 @@ struct RemapParams {
 // kernels launched to *launches.
 cudaError_t launch_fused(uint32_t stages, const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_pca_stats(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
-cudaError_t launch_pca_lut(const unsigned long long* stats, uint8_t* wb, float* coeff_out, int n_frames,
+cudaError_t launch_pca_lut(const unsigned long long* stats, float* wbf, float* coeff_out, int n_frames,
                            cudaStream_t stream, int* launches);
-cudaError_t launch_gain_lut(const float* gains_bgr, uint8_t* wb, int n_frames, cudaStream_t stream, int* launches);
+cudaError_t launch_gain_lut(const float* gains_bgr, float* wbf, int n_frames, cudaStream_t stream, int* launches);
+// Fast path (rip_fast.cu): TMA-staged tiles, packed-byte demosaic.  fast_path_ok() looks at the input side
+// (Bayer, width % 16 == 0, no 90/270 rotation, 16-byte aligned), fast_out_ok() at the output buffer.
+bool fast_path_ok(const FrameParams& p);
+bool fast_out_ok(const FrameParams& p);
+cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
+cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
 
 }  // namespace rip

@@ -33,7 +33,7 @@ thread_local std::string g_create_error;
 // per-stream scratch for one in-flight batch
 struct Scratch {
   DevBuf color;   // pre-undistortion images when the caller does not provide a buffer
-  DevBuf wb;      // n x 768
+  DevBuf wb;      // n x 3 x 256 float
   DevBuf stats;   // n x 8 u64
   DevBuf coeff;   // n x 4 float (pca coefficients, kept for inspection)
   DevBuf gains;   // n x 3 float (ccc)
@@ -73,6 +73,7 @@ struct rip_pipeline {
   enum { SPAN_STATS = 0, SPAN_LUT = 1, SPAN_FUSED = 2, SPAN_REMAP = 3, SPAN_KINDS = 4 };
   struct Span { int kind; cudaEvent_t a, b; };
   bool profile = false;
+  bool force_generic = false;  // "debug/force_generic_kernels": tests run both kernel families
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
     if (!profile) return cudaSuccess;
@@ -89,7 +90,7 @@ struct rip_pipeline {
   }
 
   // device-resident parameters
-  DevBuf d_tables; bool tables_valid = false; double tables_gamma_k = 0; double tables_enh[3] = {0, 0, 0};
+  DevBuf d_tables; bool tables_valid = false; ChainTableParams tables_key;
   DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
   DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
   std::vector<float> h_map;  // host copy (debug / tests)
@@ -215,21 +216,16 @@ int stage_mask(rip_pipeline* p, const FrameGeom& g, uint32_t& stages, int& wb_ki
 
 int ensure_tables(rip_pipeline* p) {
   const Params& q = p->hs.p;
-  const double enh[3] = {q.enh_hue_gain, q.enh_saturation_gain, q.enh_value_gain};
-  if (p->tables_valid && p->tables_gamma_k == q.gamma_k && memcmp(enh, p->tables_enh, sizeof enh) == 0) return RIP_OK;
+  ChainTableParams key;
+  key.gamma_enabled = q.gamma_enabled; key.gamma_k = q.gamma_k;
+  key.enh_gain[0] = q.enh_hue_gain; key.enh_gain[1] = q.enh_saturation_gain; key.enh_gain[2] = q.enh_value_gain;
+  if (p->tables_valid && key == p->tables_key) return RIP_OK;
   std::vector<uint8_t> blob(TABLE_BYTES, 0);
-  build_gamma_lut(q.gamma_k, blob.data() + OFF_GAMMA);
-  build_enhancer_luts(q, blob.data() + OFF_ENH);
-  memcpy(blob.data() + OFF_INVG, kSrgbInvGammaTab, sizeof kSrgbInvGammaTab);
-  memcpy(blob.data() + OFF_SRGBG, kSrgbGammaTab, sizeof kSrgbGammaTab);
-  memcpy(blob.data() + OFF_LABC, kLabCbrtTab, sizeof kLabCbrtTab);
-  memcpy(blob.data() + OFF_YF, kLabToYF, sizeof kLabToYF);
-  memcpy(blob.data() + OFF_SDIV, kHsvSdiv, sizeof kHsvSdiv);
-  memcpy(blob.data() + OFF_HDIV, kHsvHdiv, sizeof kHsvHdiv);
+  build_chain_blob(key, blob.data());
   RIP_CUDA(p, cudaDeviceSynchronize());  // nothing in flight may still read the old tables
   RIP_CUDA(p, p->d_tables.reserve(TABLE_BYTES));
   RIP_CUDA(p, cudaMemcpy(p->d_tables.ptr, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice));
-  p->tables_valid = true; p->tables_gamma_k = q.gamma_k; memcpy(p->tables_enh, enh, sizeof enh);
+  p->tables_valid = true; p->tables_key = key;
   return RIP_OK;
 }
 
@@ -240,10 +236,15 @@ int ensure_vignetting(rip_pipeline* p, int rows, int cols) {
   std::vector<float> quad;
   int qr = 0, qc = 0;
   build_vignetting_quadrant(rows, cols, q.vig_scale, q.vig_a2, q.vig_a4, quad, qr, qc);
+  // device layout: the upper half of the mask at full width, so that four horizontally adjacent pixels
+  // are one aligned 16-byte load; row qi = |2*i - rows| >> 1 serves image rows i and rows - i
+  std::vector<float> half((size_t)qr * cols);
+  for (int qi = 0; qi < qr; ++qi)
+    for (int j = 0; j < cols; ++j) half[(size_t)qi * cols + j] = quad[(size_t)qi * qc + (std::abs(2 * j - cols) >> 1)];
   RIP_CUDA(p, cudaDeviceSynchronize());
-  RIP_CUDA(p, p->d_vig.reserve(quad.size() * sizeof(float)));
-  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, quad.data(), quad.size() * sizeof(float), cudaMemcpyHostToDevice));
-  p->vig_rows = rows; p->vig_cols = cols; p->vig_pitch = qc; memcpy(p->vig_par, par, sizeof par);
+  RIP_CUDA(p, p->d_vig.reserve(half.size() * sizeof(float)));
+  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, half.data(), half.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->vig_rows = rows; p->vig_cols = cols; p->vig_pitch = cols; memcpy(p->vig_par, par, sizeof par);
   return RIP_OK;
 }
 
@@ -292,6 +293,13 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   fp.vig = p->d_vig.as<float>(); fp.vig_pitch = p->vig_pitch;
   for (int i = 0; i < 9; ++i) fp.k.cc[i] = q.cc_matrix[i];
   for (int i = 0; i < 3; ++i) fp.k.cc_bias[i] = (float)q.cc_bias[i];  // Scalar double -> fp32 on cv::add
+  fp.k.cc_has_bias = 0;
+  for (int i = 0; i < 3; ++i) {
+    uint32_t bits;
+    memcpy(&bits, &fp.k.cc_bias[i], 4);
+    if (bits != 0) fp.k.cc_has_bias = 1;  // anything but +0.0f (NaN and -0.0f included) keeps the add
+  }
+  fp.k.wb_g_identity = 0;
   const size_t color_frame = (size_t)g.frows * g.fcols * 3;
   if (undistort) {
     if (d_color_user) { fp.out = d_color_user; }
@@ -302,27 +310,31 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   }
   fp.out_pitch = g.fcols * 3;
 
+  const bool fast_in = !p->force_generic && fast_path_ok(fp);
   if (stages & ST_WB) {
-    RIP_CUDA(p, sc.wb.reserve((size_t)n * 768));
-    fp.wb = sc.wb.as<uint8_t>();
+    RIP_CUDA(p, sc.wb.reserve((size_t)n * 768 * sizeof(float)));
+    fp.wbf = sc.wb.as<float>();
+    fp.k.wb_g_identity = wb_kind == 1 ? 1 : 0;  // pca leaves G untouched (white_balance.cpp:117-127)
     if (wb_kind == 1) {
       RIP_CUDA(p, sc.stats.reserve((size_t)n * 8 * sizeof(unsigned long long)));
       RIP_CUDA(p, sc.coeff.reserve((size_t)n * 4 * sizeof(float)));
       fp.stats = sc.stats.as<unsigned long long>();
       RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_STATS, stream));
-      RIP_CUDA(p, launch_pca_stats(fp, p->sm_count, stream, &launches));
+      if (fast_in) RIP_CUDA(p, launch_pca_stats_fast(fp, p->sm_count, stream, &launches));
+      else RIP_CUDA(p, launch_pca_stats(fp, p->sm_count, stream, &launches));
       RIP_CUDA(p, p->span_end(stream));
       RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_LUT, stream));
-      RIP_CUDA(p, launch_pca_lut(fp.stats, sc.wb.as<uint8_t>(), sc.coeff.as<float>(), n, stream, &launches));
+      RIP_CUDA(p, launch_pca_lut(fp.stats, sc.wb.as<float>(), sc.coeff.as<float>(), n, stream, &launches));
       RIP_CUDA(p, p->span_end(stream));
     } else {
       int rc = ccc_white_balance(p->ccc, q, fp, sc.ccc, sc.gains, p->sm_count, stream, &launches, p->last_error);
       if (rc != RIP_OK) return rc;
-      RIP_CUDA(p, launch_gain_lut(static_cast<const float*>(sc.gains.ptr), sc.wb.as<uint8_t>(), n, stream, &launches));
+      RIP_CUDA(p, launch_gain_lut(static_cast<const float*>(sc.gains.ptr), sc.wb.as<float>(), n, stream, &launches));
     }
   }
   RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
-  RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
+  if (fast_in && fast_out_ok(fp)) RIP_CUDA(p, launch_fused_fast(stages, fp, p->sm_count, stream, &launches));
+  else RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
   RIP_CUDA(p, p->span_end(stream));
   if (undistort) {
     RemapParams rp{};
@@ -435,6 +447,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   if (key_is(key, "gpu")) q.use_gpu = v;
   else if (key_is(key, "debug")) q.debug = v;
   else if (key_is(key, "profile/kernel_events")) p->profile = v;
+  else if (key_is(key, "debug/force_generic_kernels")) p->force_generic = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;

@@ -1,0 +1,427 @@
+// Fast path of the fused chain and of the PCA statistics for the shapes cameras actually deliver
+// (8-bit Bayer, width a multiple of 16, no 90/270 rotation, 16-byte aligned buffers):
+//
+//   * Bayer tiles (128 x 32 px + halo, 160 B x 34 rows) are brought into shared memory by the TMA
+//     unit (cp.async.bulk.tensor, zero fill outside the frame), double buffered behind mbarriers so the
+//     load of tile i+1 runs under the arithmetic of tile i;
+//   * the demosaic stencil runs on packed bytes (4 px per 32-bit word, frame_math.cuh demosaic_quad_swar);
+//   * the BGR8 tile is assembled in shared memory and leaves through one TMA store per tile
+//     (cp.async.bulk.tensor ... bulk_group), double buffered, clipped to the frame by the hardware;
+//   * persistent grid: resident CTAs walk the tile list of the whole batch frame-major.
+//
+// Everything else (ragged widths, unaligned buffers, 90/270 rotations, 3-channel inputs) takes the
+// generic kernels in rip_kernels.cu; both produce identical bytes.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "frame_math.cuh"
+#include "kernels.hpp"
+
+namespace rip {
+
+namespace {
+
+constexpr int TW = 128, TH = 32, NT = 256;
+// The TMA unit needs the innermost coordinate 16-byte aligned (probed: tools/tma_probe, unaligned x traps with
+// "illegal instruction"), so the 1-pixel halo is fetched as a 16-byte column on each side.
+constexpr int IN_PITCH = 160;           // staged Bayer row: columns x0-16 .. x0+143
+constexpr int IN_WORDS = IN_PITCH / 4;  // 40
+constexpr int IN_X_WORD0 = 3;           // word holding columns x0-4 .. x0-1
+constexpr int IN_ROWS = TH + 2;         // rows y0-1 .. y0+TH
+constexpr int IN_BYTES = IN_PITCH * IN_ROWS;            // 5440 = what one TMA load delivers
+constexpr int IN_BUF = (IN_BYTES + 127) / 128 * 128;    // 5504
+constexpr int OUT_PITCH = TW * 3;                       // 384
+constexpr int OUT_BUF = OUT_PITCH * TH;                 // 12288
+
+struct FastSmem {
+  alignas(128) uint8_t in[2][IN_BUF];
+  alignas(128) uint8_t out[2][OUT_BUF];
+  alignas(16) uint8_t tables[TABLE_BYTES];
+  alignas(16) float wbf[768];
+  alignas(8) unsigned long long mbar[2];
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Tiles are enumerated on a grid anchored at the origin of the OUTPUT frame (TMA stores do not take negative
+// coordinates; loads do, with zero fill).  (x0, y0) is the tile's origin in the INPUT frame: equal to the output
+// origin without rotation, mirrored -- and possibly negative for the partial edge tiles -- for 180 degrees.
+struct TileCoord {
+  int frame, x0, y0, ox0, oy0;
+};
+__device__ __forceinline__ TileCoord tile_coord(long long t, int tiles_x, long long tiles_per_frame, bool rev, int rows, int cols) {
+  TileCoord c;
+  c.frame = (int)(t / tiles_per_frame);
+  const int rem = (int)(t - (long long)c.frame * tiles_per_frame);
+  const int ty = rem / tiles_x;
+  c.ox0 = (rem - ty * tiles_x) * TW;
+  c.oy0 = ty * TH;
+  c.x0 = rev ? cols - c.ox0 - TW : c.ox0;
+  c.y0 = rev ? rows - c.oy0 - TH : c.oy0;
+  return c;
+}
+
+// packed B / G / R words of the four pixels (y, x .. x+3); `s_in` is the staged tile whose row 0 is y0 - 1
+__device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, int cols, int cfa, int y0, int y, int x, int lane,
+                                               uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const int yc = y < 1 ? 1 : (y > rows - 2 ? rows - 2 : y);  // OpenCV's border rule (frame_math.cuh demosaic_at)
+  const uint32_t* p = s_in + (yc - y0) * IN_WORDS + IN_X_WORD0 + lane;  // staged row of yc - 1, word of columns x-4..x-1
+  uint32_t w[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w[a][j] = p[a * IN_WORDS + j];
+  const bool row_has_r = ((yc & 1) == ((cfa >> 1) & 1));
+  const int cpar = row_has_r ? (cfa & 1) : ((cfa & 1) ^ 1);
+  demosaic_quad_swar(w, row_has_r, cpar, Bw, Gw, Rw);
+  if (x == 0) {  // column 0 <- column 1
+    Bw = prmt(Bw, 0u, 0x3211u); Gw = prmt(Gw, 0u, 0x3211u); Rw = prmt(Rw, 0u, 0x3211u);
+  }
+  if (x + 4 == cols) {  // column W-1 <- column W-2
+    Bw = prmt(Bw, 0u, 0x2210u); Gw = prmt(Gw, 0u, 0x2210u); Rw = prmt(Rw, 0u, 0x2210u);
+  }
+}
+
+// =============================================================================================
+// fused kernel, fast path
+// =============================================================================================
+template <uint32_t STAGES>
+__global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map,
+                                                   const __grid_constant__ CUtensorMap out_map) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
+  const long long tiles_per_frame = (long long)tiles_x * tiles_y;
+  const long long total = tiles_per_frame * P.n_frames;
+  const bool rev = P.angle == 180;
+
+  if (tid == 0) {
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    fence_mbar_init();
+  }
+  if (STAGES & (ST_GAMMA | ST_VIG | ST_ENH)) {
+    const uint4* src = reinterpret_cast<const uint4*>(P.tables);
+    uint4* dst = reinterpret_cast<uint4*>(sm.tables);
+    for (int i = tid; i < TABLE_BYTES / 16; i += NT) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const ChainTables T = chain_tables_from_blob(sm.tables, sm.wbf);
+
+  long long t = blockIdx.x;
+  if (t < total && tid == 0) {
+    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    mbar_expect_tx(&sm.mbar[0], IN_BYTES);
+    tma_load_3d(sm.in[0], &in_map, &sm.mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
+  }
+  int cur_frame = -1;
+  const int tail_start = P.ocols & ~31;  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
+
+  for (int it = 0; t < total; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    if (tid == 0) {
+      const long long tn = t + gridDim.x;
+      if (tn < total) {  // in[buf ^ 1] was last read before the barrier that ended iteration it - 1
+        const TileCoord cn = tile_coord(tn, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+        mbar_expect_tx(&sm.mbar[buf ^ 1], IN_BYTES);
+        tma_load_3d(sm.in[buf ^ 1], &in_map, &sm.mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
+      }
+      tma_wait_read<1>();  // the store that read out[buf] two iterations ago has drained
+    }
+    if ((STAGES & ST_WB) && c.frame != cur_frame) {
+      const float* src = P.wbf + (size_t)c.frame * 768;
+      for (int i = tid; i < 768; i += NT) sm.wbf[i] = src[i];  // plain load: written by a prior kernel
+      cur_frame = c.frame;
+    }
+    __syncthreads();  // out[buf] reusable, wbf visible
+    mbar_wait(&sm.mbar[buf], (uint32_t)(it >> 1) & 1u);
+
+    const uint32_t* s_in = reinterpret_cast<const uint32_t*>(sm.in[buf]);
+    uint8_t* s_out = sm.out[buf];
+    const int x = c.x0 + 4 * lane;
+#pragma unroll 1
+    for (int rr = 0; rr < TH / 8; ++rr) {
+      const int r_in_tile = warp + 8 * rr;
+      const int y = c.y0 + r_in_tile;
+      if (y < 0 || y >= P.rows || x < 0 || x >= P.cols) continue;
+      uint32_t Bw, Gw, Rw;
+      quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
+      const int oy = rev ? P.rows - 1 - y : y;
+      const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
+      float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+      if (STAGES & ST_VIG) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch + oxb));
+        if (rev) { m[0] = v.w; m[1] = v.z; m[2] = v.y; m[3] = v.x; } else { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+      }
+      uint32_t px[4];
+      if ((STAGES & ST_ENH) && oxb >= tail_start) {  // whole quad lies in cv2's scalar row tail (rare: width % 32 != 0)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          px[k] = chain_pixel<STAGES>((Bw >> (8 * k)) & 255, (Gw >> (8 * k)) & 255, (Rw >> (8 * k)) & 255, m[k], true, P.k, T);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          px[k] = chain_pixel<STAGES>((Bw >> (8 * k)) & 255, (Gw >> (8 * k)) & 255, (Rw >> (8 * k)) & 255, m[k], false, P.k, T);
+      }
+      if (!rev) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(s_out + r_in_tile * OUT_PITCH + 12 * lane);
+        o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542);
+      } else {  // 180: mirrored inside the tile, pixel order reversed
+        uint32_t* o = reinterpret_cast<uint32_t*>(s_out + (TH - 1 - r_in_tile) * OUT_PITCH + 12 * (31 - lane));
+        o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542);
+      }
+    }
+    fence_async_smem();  // make this thread's shared-memory writes visible to the TMA unit
+    __syncthreads();
+    if (tid == 0) {
+      // the TMA unit clips rows/columns beyond the tensor; 4-byte elements
+      tma_store_3d(&out_map, s_out, (c.ox0 * 3) / 4, c.oy0, c.frame);
+      tma_commit();
+    }
+  }
+  if (tid == 0) tma_wait_read<0>();  // shared memory must stay valid until the last store has read it
+}
+
+// =============================================================================================
+// PCA white-balance statistics, fast path (white_balance.cpp:89-102)
+// =============================================================================================
+__device__ __forceinline__ unsigned dp4a_u(uint32_t a, uint32_t b, unsigned c) { return __dp4a(a, b, c); }
+
+__global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map) {
+  __shared__ alignas(128) uint8_t s_inb[2][IN_BUF];
+  __shared__ alignas(8) unsigned long long mbar[2];
+  __shared__ unsigned long long s_acc[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
+  const long long tiles_per_frame = (long long)tiles_x * tiles_y;
+  const long long total = tiles_per_frame * P.n_frames;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  if (tid < 8) s_acc[tid] = 0;
+  __syncthreads();
+  const bool rev = false;  // sums and maxima do not depend on the rotation
+  long long t = blockIdx.x;
+  if (t < total && tid == 0) {
+    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    mbar_expect_tx(&mbar[0], IN_BYTES);
+    tma_load_3d(s_inb[0], &in_map, &mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
+  }
+  int cur_frame = -1;
+  // per-thread partial results of the current frame
+  unsigned sb = 0, sr = 0, sg = 0;             // sums of <= 2^? values: flushed per tile (see below)
+  unsigned long long sb2 = 0, sr2 = 0;
+  uint32_t mx_b = 0, mx_g = 0, mx_r = 0;       // packed per-byte maxima (two 16-bit lanes x even/odd bytes folded below)
+
+  auto flush = [&](int frame) {
+    // fold the packed maxima to scalars, reduce over the warp, one shared atomic per warp, then one global per CTA
+    unsigned mb = max(max(mx_b & 0xffu, (mx_b >> 8) & 0xffu), max((mx_b >> 16) & 0xffu, mx_b >> 24));
+    unsigned mg = max(max(mx_g & 0xffu, (mx_g >> 8) & 0xffu), max((mx_g >> 16) & 0xffu, mx_g >> 24));
+    unsigned mr = max(max(mx_r & 0xffu, (mx_r >> 8) & 0xffu), max((mx_r >> 16) & 0xffu, mx_r >> 24));
+    unsigned long long vb = sb, vr = sr, vg = sg, vb2 = sb2, vr2 = sr2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vb += __shfl_xor_sync(0xffffffffu, vb, o); vr += __shfl_xor_sync(0xffffffffu, vr, o); vg += __shfl_xor_sync(0xffffffffu, vg, o);
+      vb2 += __shfl_xor_sync(0xffffffffu, vb2, o); vr2 += __shfl_xor_sync(0xffffffffu, vr2, o);
+    }
+    mb = __reduce_max_sync(0xffffffffu, mb); mg = __reduce_max_sync(0xffffffffu, mg); mr = __reduce_max_sync(0xffffffffu, mr);
+    if (lane == 0) {
+      atomicAdd(&s_acc[0], vb); atomicAdd(&s_acc[1], vb2); atomicAdd(&s_acc[2], vr); atomicAdd(&s_acc[3], vr2); atomicAdd(&s_acc[4], vg);
+      atomicMax(&s_acc[5], (unsigned long long)mb); atomicMax(&s_acc[6], (unsigned long long)mg); atomicMax(&s_acc[7], (unsigned long long)mr);
+    }
+    __syncthreads();
+    if (tid < 8) {
+      unsigned long long* dst = P.stats + (size_t)frame * 8 + tid;
+      if (tid < 5) atomicAdd(dst, s_acc[tid]); else atomicMax(dst, s_acc[tid]);
+      s_acc[tid] = 0;
+    }
+    __syncthreads();
+    sb = sr = sg = 0; sb2 = sr2 = 0; mx_b = mx_g = mx_r = 0;
+  };
+
+  for (int it = 0; t < total; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    if (cur_frame >= 0 && c.frame != cur_frame) flush(cur_frame);  // uniform over the CTA
+    cur_frame = c.frame;
+    __syncthreads();  // everyone is done reading in[buf ^ 1]
+    if (tid == 0) {
+      const long long tn = t + gridDim.x;
+      if (tn < total) {
+        const TileCoord cn = tile_coord(tn, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+        mbar_expect_tx(&mbar[buf ^ 1], IN_BYTES);
+        tma_load_3d(s_inb[buf ^ 1], &in_map, &mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
+      }
+    }
+    mbar_wait(&mbar[buf], (uint32_t)(it >> 1) & 1u);
+    const uint32_t* s_in = reinterpret_cast<const uint32_t*>(s_inb[buf]);
+    const int x = c.x0 + 4 * lane;
+    unsigned tb2 = 0, tr2 = 0;  // 4 rows x 4 px x 255^2 < 2^21
+#pragma unroll
+    for (int rr = 0; rr < TH / 8; ++rr) {
+      const int y = c.y0 + warp + 8 * rr;
+      if (y >= P.rows || x >= P.cols) continue;
+      uint32_t Bw, Gw, Rw;
+      quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
+      sb = dp4a_u(Bw, 0x01010101u, sb); sr = dp4a_u(Rw, 0x01010101u, sr); sg = dp4a_u(Gw, 0x01010101u, sg);
+      tb2 = dp4a_u(Bw, Bw, tb2); tr2 = dp4a_u(Rw, Rw, tr2);
+      mx_b = __vmaxu4(mx_b, Bw); mx_g = __vmaxu4(mx_g, Gw); mx_r = __vmaxu4(mx_r, Rw);
+    }
+    sb2 += tb2; sr2 += tr2;
+    // sb/sr/sg grow by <= 16 * 255 per tile: a CTA walks < 2^20 tiles of one frame, no overflow before the flush
+  }
+  if (cur_frame >= 0) flush(cur_frame);
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap* map, CUtensorMapDataType type, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t stride1,
+              cuuint64_t stride2, cuuint32_t b0, cuuint32_t b1) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {stride1, stride2};
+  const cuuint32_t box[3] = {b0, b1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, type, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool in_map_for(const FrameParams& p, CUtensorMap* map) {
+  // a single frame still needs a legal stride for the (unused) frame dimension
+  const cuuint64_t fstride = p.n_frames > 1 ? (cuuint64_t)p.in_frame_stride : (cuuint64_t)p.in_pitch * p.rows;
+  return make_map(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, p.in, (cuuint64_t)p.cols, (cuuint64_t)p.rows, (cuuint64_t)p.n_frames,
+                  (cuuint64_t)p.in_pitch, fstride, IN_PITCH, IN_ROWS);
+}
+
+long long total_tiles(const FrameParams& p) {
+  return (long long)((p.cols + TW - 1) / TW) * ((p.rows + TH - 1) / TH) * p.n_frames;
+}
+
+template <uint32_t S>
+cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorMap& im, const CUtensorMap& om, int sm_count,
+                          cudaStream_t stream) {
+  if (stages == S) {
+    static int occ = 0;  // per instantiation
+    if (occ == 0) {
+      cudaError_t e = cudaFuncSetAttribute(k_fused_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+      if (e != cudaSuccess) return e;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S>, NT, sizeof(FastSmem));
+      if (e != cudaSuccess) return e;
+      if (occ < 1) occ = 1;
+    }
+    const long long tiles = total_tiles(p), cap = (long long)sm_count * occ;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    k_fused_fast<S><<<grid, NT, sizeof(FastSmem), stream>>>(p, im, om);
+    return cudaGetLastError();
+  }
+  if constexpr (S < ST_ALL) return dispatch_fast<S + 1>(stages, p, im, om, sm_count, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool fast_path_ok(const FrameParams& p) {
+  if (p.src != SRC_BAYER || !(p.angle == 0 || p.angle == 180)) return false;
+  if (p.cols % 16 != 0 || p.cols < 16 || p.rows < 3 || p.n_frames < 1) return false;
+  if (p.in_pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(p.in) & 15) != 0) return false;
+  if (p.n_frames > 1 && (p.in_frame_stride % 16 != 0 || p.in_frame_stride <= 0)) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+bool fast_out_ok(const FrameParams& p) {
+  if (p.out_pitch != p.ocols * 3 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
+  if (p.n_frames > 1 && (p.out_frame_stride % 16 != 0 || p.out_frame_stride <= 0)) return false;
+  return true;
+}
+
+cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, int sm_count, cudaStream_t stream, int* launches) {
+  CUtensorMap im, om;
+  if (!in_map_for(p, &im)) return cudaErrorInvalidValue;
+  const cuuint64_t ofs = p.n_frames > 1 ? (cuuint64_t)p.out_frame_stride : (cuuint64_t)p.out_pitch * p.orows;
+  if (!make_map(&om, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.out, (cuuint64_t)(p.ocols * 3 / 4), (cuuint64_t)p.orows, (cuuint64_t)p.n_frames,
+                (cuuint64_t)p.out_pitch, ofs, OUT_PITCH / 4, TH))
+    return cudaErrorInvalidValue;
+  if (launches) ++*launches;
+  return dispatch_fast<0>(stages & ST_ALL, p, im, om, sm_count, stream);
+}
+
+cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches) {
+  CUtensorMap im;
+  if (!in_map_for(p, &im)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * 8 * p.n_frames, stream);
+  if (e != cudaSuccess) return e;
+  static int occ = 0;
+  if (occ == 0) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pca_stats_fast, NT, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+  }
+  const long long tiles = total_tiles(p), cap = (long long)sm_count * occ;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  if (launches) ++*launches;
+  k_pca_stats_fast<<<grid, NT, 0, stream>>>(p, im);
+  return cudaGetLastError();
+}
+
+}  // namespace rip

@@ -31,24 +31,10 @@ constexpr int OUT_ROW_BYTES = TW * 3;
 
 struct __align__(16) SmemFused {
   uint8_t tables[TABLE_BYTES];
-  uint8_t wb[768];
+  float wbf[768];
   uint32_t in[IN_ROWS * IN_WORDS];
   uint8_t out[TH * OUT_ROW_BYTES];
 };
-
-__device__ __forceinline__ ChainTables tables_from_smem(const uint8_t* t, const uint8_t* wb) {
-  ChainTables c;
-  c.wb = wb;
-  c.gamma = t + OFF_GAMMA;
-  c.enh = t + OFF_ENH;
-  c.inv_g = t + OFF_INVG;
-  c.srgb_g = reinterpret_cast<const uint16_t*>(t + OFF_SRGBG);
-  c.lab_c = reinterpret_cast<const uint16_t*>(t + OFF_LABC);
-  c.lab_yf = reinterpret_cast<const uint32_t*>(t + OFF_YF);
-  c.sdiv = reinterpret_cast<const int32_t*>(t + OFF_SDIV);
-  c.hdiv = reinterpret_cast<const int32_t*>(t + OFF_HDIV);
-  return c;
-}
 
 // destination (post-flip) coordinate of input pixel (iy, ix): inverse of flip_source()
 __device__ __forceinline__ void flip_dest(int angle, int rows, int cols, int iy, int ix, int& oy, int& ox) {
@@ -161,6 +147,46 @@ __device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int n
 // =============================================================================================
 // fused kernel
 // =============================================================================================
+// vignetting-mask values and cv2 row-tail flags of the four pixels (y, x..x+3) a thread owns
+template <uint32_t STAGES>
+__device__ __forceinline__ void quad_position_inputs(const FrameParams& P, int y, int x, float m[4], bool tail[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { m[k] = 1.0f; tail[k] = false; }
+  if (!(STAGES & (ST_VIG | ST_ENH))) return;
+  const int tail_start = P.ocols & ~31;  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
+  if (P.angle == 0 || P.angle == 180) {
+    const bool rev = P.angle == 180;
+    const int oy = rev ? P.rows - 1 - y : y;
+    const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
+    if (STAGES & ST_VIG) {
+      const float* mrow = P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch;
+      if (x + 3 < P.cols && ((P.vig_pitch | oxb) & 3) == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(mrow + oxb));
+        if (rev) { m[0] = v.w; m[1] = v.z; m[2] = v.y; m[3] = v.x; } else { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (x + k < P.cols) m[k] = __ldg(mrow + (rev ? P.cols - 1 - x - k : x + k));
+      }
+    }
+    if (STAGES & ST_ENH) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tail[k] = (rev ? P.cols - 1 - x - k : x + k) >= tail_start;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int oy, ox;
+      flip_dest(P.angle, P.rows, P.cols, y, min(x + k, P.cols - 1), oy, ox);
+      if (STAGES & ST_VIG) m[k] = __ldg(P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch + ox);
+      tail[k] = ox >= tail_start;
+    }
+  }
+}
+
+// =============================================================================================
+// fused kernel
+// =============================================================================================
 template <uint32_t STAGES, int SRC>
 __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ FrameParams P) {
   __shared__ SmemFused sm;
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ Fram
     uint4* dst = reinterpret_cast<uint4*>(sm.tables);
     for (int i = threadIdx.x; i < TABLE_BYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
   }
-  const ChainTables T = tables_from_smem(sm.tables, sm.wb);
+  const ChainTables T = chain_tables_from_blob(sm.tables, sm.wbf);
   const bool in_aligned4 = ((reinterpret_cast<uintptr_t>(P.in) | (uintptr_t)P.in_pitch | (uintptr_t)P.in_frame_stride) & 3) == 0;
   const bool staged_out = (P.angle == 0 || P.angle == 180);
   int cur_frame = -1;
@@ -189,9 +215,8 @@ __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ Fram
 
     __syncthreads();  // previous tile fully copied out / tables visible
     if ((STAGES & ST_WB) && frame != cur_frame) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.wb + (size_t)frame * 768);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(sm.wb);
-      for (int i = threadIdx.x; i < 768 / 4; i += NTHREADS) dst[i] = src[i];  // plain load: written by a prior kernel
+      const float* src = P.wbf + (size_t)frame * 768;
+      for (int i = threadIdx.x; i < 768; i += NTHREADS) sm.wbf[i] = src[i];  // plain load: written by a prior kernel
       cur_frame = frame;
     }
     if (SRC == SRC_BAYER) stage_bayer_tile(sm.in, fin, P.in_pitch, P.rows, P.cols, y0, x0, in_aligned4);
@@ -205,32 +230,19 @@ __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ Fram
       if (y >= P.rows || x >= P.cols) continue;
       int b[4], g[4], r[4];
       fetch_quad<SRC>(P, fin, sm.in, y0, y, x, lane, in_aligned4, b, g, r);
+      float m[4];
+      bool tail[4];
+      quad_position_inputs<STAGES>(P, y, x, m, tail);
+      uint32_t px[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float m = 1.0f;
-        bool row_tail = false;
-        if (STAGES & (ST_VIG | ST_ENH)) {  // stages that depend on the post-flip pixel position
-          int oy, ox;
-          flip_dest(P.angle, P.rows, P.cols, y, min(x + k, P.cols - 1), oy, ox);
-          if (STAGES & ST_VIG) {
-            const int qi = abs(2 * oy - P.orows) >> 1, qj = abs(2 * ox - P.ocols) >> 1;
-            m = __ldg(P.vig + (size_t)qi * P.vig_pitch + qj);
-          }
-          row_tail = ox >= (P.ocols & ~31);  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
-        }
-        chain_pixel<STAGES>(b[k], g[k], r[k], m, row_tail, P.k, T);
-      }
+      for (int k = 0; k < 4; ++k) px[k] = chain_pixel<STAGES>(b[k], g[k], r[k], m[k], tail[k], P.k, T);
       if (staged_out) {
         if (P.angle == 0) {
           uint32_t* o = reinterpret_cast<uint32_t*>(sm.out + r_in_tile * OUT_ROW_BYTES + 12 * lane);
-          o[0] = (uint32_t)b[0] | ((uint32_t)g[0] << 8) | ((uint32_t)r[0] << 16) | ((uint32_t)b[1] << 24);
-          o[1] = (uint32_t)g[1] | ((uint32_t)r[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)g[2] << 24);
-          o[2] = (uint32_t)r[2] | ((uint32_t)b[3] << 8) | ((uint32_t)g[3] << 16) | ((uint32_t)r[3] << 24);
+          o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542);
         } else {  // 180: mirrored inside the tile, pixel order reversed
           uint32_t* o = reinterpret_cast<uint32_t*>(sm.out + (TH - 1 - r_in_tile) * OUT_ROW_BYTES + 12 * (31 - lane));
-          o[0] = (uint32_t)b[3] | ((uint32_t)g[3] << 8) | ((uint32_t)r[3] << 16) | ((uint32_t)b[2] << 24);
-          o[1] = (uint32_t)g[2] | ((uint32_t)r[2] << 8) | ((uint32_t)b[1] << 16) | ((uint32_t)g[1] << 24);
-          o[2] = (uint32_t)r[1] | ((uint32_t)b[0] << 8) | ((uint32_t)g[0] << 16) | ((uint32_t)r[0] << 24);
+          o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542);
         }
       } else {  // 90 / 270: scattered byte stores (rare mode; correctness path)
 #pragma unroll
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS) k_fused(const __grid_constant__ Fram
           int oy, ox;
           flip_dest(P.angle, P.rows, P.cols, y, x + k, oy, ox);
           uint8_t* o = fout + (size_t)oy * P.out_pitch + 3 * ox;
-          o[0] = (uint8_t)b[k]; o[1] = (uint8_t)g[k]; o[2] = (uint8_t)r[k];
+          o[0] = (uint8_t)px[k]; o[1] = (uint8_t)(px[k] >> 8); o[2] = (uint8_t)(px[k] >> 16);
         }
       }
     }
@@ -328,26 +340,27 @@ __global__ void __launch_bounds__(NTHREADS) k_pca_stats(const __grid_constant__ 
   }
 }
 
-// one CTA per frame: thread x builds LUT entry x for B and R (G stays identity)
-__global__ void __launch_bounds__(256) k_pca_lut(const unsigned long long* __restrict__ stats, uint8_t* __restrict__ wb,
+// one CTA per frame: thread x builds LUT entry x for B and R (G stays identity); entries are stored as
+// floats (exact integers) because their consumer is the fp32 colour-calibration mix
+__global__ void __launch_bounds__(256) k_pca_lut(const unsigned long long* __restrict__ stats, float* __restrict__ wbf,
                                                 float* __restrict__ coeff_out) {
   const int frame = blockIdx.x, x = threadIdx.x;
   const PcaCoeff c = pca_coefficients(stats + (size_t)frame * 8);
-  uint8_t* lut = wb + (size_t)frame * 768;
-  lut[x] = (uint8_t)pca_lut_entry(x, c.alpha_b, c.beta_b);
-  lut[256 + x] = (uint8_t)x;
-  lut[512 + x] = (uint8_t)pca_lut_entry(x, c.alpha_r, c.beta_r);
+  float* lut = wbf + (size_t)frame * 768;
+  lut[x] = (float)pca_lut_entry(x, c.alpha_b, c.beta_b);
+  lut[256 + x] = (float)x;
+  lut[512 + x] = (float)pca_lut_entry(x, c.alpha_r, c.beta_r);
   if (coeff_out && x == 0) {
     float* o = coeff_out + (size_t)frame * 4;
     o[0] = c.alpha_b; o[1] = c.beta_b; o[2] = c.alpha_r; o[3] = c.beta_r;
   }
 }
 
-__global__ void __launch_bounds__(256) k_gain_lut(const float* __restrict__ gains_bgr, uint8_t* __restrict__ wb) {
+__global__ void __launch_bounds__(256) k_gain_lut(const float* __restrict__ gains_bgr, float* __restrict__ wbf) {
   const int frame = blockIdx.x, x = threadIdx.x;
-  uint8_t* lut = wb + (size_t)frame * 768;
+  float* lut = wbf + (size_t)frame * 768;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) lut[256 * c + x] = (uint8_t)gain_lut_entry(x, gains_bgr[(size_t)frame * 3 + c]);
+  for (int c = 0; c < 3; ++c) lut[256 * c + x] = (float)gain_lut_entry(x, gains_bgr[(size_t)frame * 3 + c]);
 }
 
 // =============================================================================================
@@ -444,18 +457,18 @@ cudaError_t launch_pca_stats(const FrameParams& p, int sm_count, cudaStream_t st
   return cudaGetLastError();
 }
 
-cudaError_t launch_pca_lut(const unsigned long long* stats, uint8_t* wb, float* coeff_out, int n_frames,
+cudaError_t launch_pca_lut(const unsigned long long* stats, float* wbf, float* coeff_out, int n_frames,
                            cudaStream_t stream, int* launches) {
   if (n_frames <= 0) return cudaSuccess;
   if (launches) ++*launches;
-  k_pca_lut<<<n_frames, 256, 0, stream>>>(stats, wb, coeff_out);
+  k_pca_lut<<<n_frames, 256, 0, stream>>>(stats, wbf, coeff_out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_gain_lut(const float* gains_bgr, uint8_t* wb, int n_frames, cudaStream_t stream, int* launches) {
+cudaError_t launch_gain_lut(const float* gains_bgr, float* wbf, int n_frames, cudaStream_t stream, int* launches) {
   if (n_frames <= 0) return cudaSuccess;
   if (launches) ++*launches;
-  k_gain_lut<<<n_frames, 256, 0, stream>>>(gains_bgr, wb);
+  k_gain_lut<<<n_frames, 256, 0, stream>>>(gains_bgr, wbf);
   return cudaGetLastError();
 }
 

@@ -3,37 +3,53 @@
 // exhaustively with cv2 before the CUDA build ever meets a GPU.  Never linked into, loaded
 // by, or shipped with the product library (raw_image_pipeline_b200/librip_b200.so).
 #include <cstring>
+#include <vector>
 #include "../../raw_image_pipeline_b200/csrc/ccc_math.cuh"
-#include "../../raw_image_pipeline_b200/csrc/cv_tables.inc"
+#include "../../raw_image_pipeline_b200/csrc/chain_tables.hpp"
 
 using namespace rip;
 
-static ChainTables make_tables(const uint8_t* wb, const uint8_t* gamma) {
-  ChainTables t;
-  t.wb = wb; t.gamma = gamma;
-  t.srgb_g = kSrgbGammaTab; t.lab_c = kLabCbrtTab; t.lab_yf = kLabToYF; t.inv_g = kSrgbInvGammaTab;
-  t.sdiv = kHsvSdiv; t.hdiv = kHsvHdiv; t.enh = nullptr;
-  return t;
+// blob with the enhancer gains folded in; `gamma` (optional) replaces the gamma LUT and is folded into g2
+static std::vector<uint8_t> make_blob(const double* enh, const uint8_t* gamma) {
+  ChainTableParams q;
+  if (enh) { q.enh_gain[0] = enh[0]; q.enh_gain[1] = enh[1]; q.enh_gain[2] = enh[2]; }
+  std::vector<uint8_t> blob(TABLE_BYTES);
+  build_chain_blob(q, blob.data());
+  if (gamma) {
+    memcpy(blob.data() + OFF_GAMMA, gamma, 256);
+    uint16_t* g2 = reinterpret_cast<uint16_t*>(blob.data() + OFF_G2);
+    for (int i = 0; i < 256; ++i) g2[i] = kSrgbGammaTab[gamma[i]];
+  }
+  return blob;
 }
 
 extern "C" {
 
+// raw (unclamped) L, a, b as int32 triples: the kernels rely on them being 0..255 already
+void hs_bgr2lab_raw(long n, const uint8_t* in, int* out) {
+  const std::vector<uint8_t> blob = make_blob(nullptr, nullptr);
+  const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
+  for (long i = 0; i < n; ++i) bgr_to_lab(in[3 * i], in[3 * i + 1], in[3 * i + 2], t.g2, t.lab_c, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
 void hs_bgr2lab(long n, const uint8_t* in, uint8_t* out) {
-  ChainTables t = make_tables(nullptr, nullptr);
+  const std::vector<uint8_t> blob = make_blob(nullptr, nullptr);
+  const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
   for (long i = 0; i < n; ++i) {
-    int L, A, B; bgr_to_lab(in[3 * i], in[3 * i + 1], in[3 * i + 2], t, L, A, B);
+    int L, A, B; bgr_to_lab(in[3 * i], in[3 * i + 1], in[3 * i + 2], t.g2, t.lab_c, L, A, B);
     out[3 * i] = L; out[3 * i + 1] = A; out[3 * i + 2] = B;
   }
 }
 void hs_lab2bgr(long n, const uint8_t* in, uint8_t* out) {
-  ChainTables t = make_tables(nullptr, nullptr);
+  const std::vector<uint8_t> blob = make_blob(nullptr, nullptr);
+  const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
   for (long i = 0; i < n; ++i) {
     int b, g, r; lab_to_bgr(in[3 * i], in[3 * i + 1], in[3 * i + 2], t, b, g, r);
     out[3 * i] = b; out[3 * i + 1] = g; out[3 * i + 2] = r;
   }
 }
 void hs_bgr2hsv(long n, const uint8_t* in, uint8_t* out) {
-  ChainTables t = make_tables(nullptr, nullptr);
+  const std::vector<uint8_t> blob = make_blob(nullptr, nullptr);
+  const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
   for (long i = 0; i < n; ++i) {
     int h, s, v; bgr_to_hsv(in[3 * i], in[3 * i + 1], in[3 * i + 2], t, h, s, v);
     out[3 * i] = h; out[3 * i + 1] = s; out[3 * i + 2] = v;
@@ -41,36 +57,48 @@ void hs_bgr2hsv(long n, const uint8_t* in, uint8_t* out) {
 }
 // `width`: row length of the image the n pixels form (selects OpenCV's scalar row tail)
 void hs_hsv2bgr(long n, int width, const uint8_t* in, uint8_t* out) {
+  const std::vector<uint8_t> blob = make_blob(nullptr, nullptr);  // unit gains
+  const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
   for (long i = 0; i < n; ++i) {
     const bool tail = (int)(i % width) >= (width & ~31);
-    int b, g, r; hsv_to_bgr(in[3 * i], in[3 * i + 1], in[3 * i + 2], tail, b, g, r);
-    out[3 * i] = b; out[3 * i + 1] = g; out[3 * i + 2] = r;
+    const uint32_t p = hsv_gain_to_bgr(in[3 * i], in[3 * i + 1], in[3 * i + 2], tail, t);
+    out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
   }
 }
 
-// full per-pixel chain; mask may be null when ST_VIG is off
+// full per-pixel chain exactly as the fused kernel runs it; mask may be null when ST_VIG is off
 void hs_chain(unsigned stages, long n, int width, const uint8_t* in, const float* mask, const float* cc, const float* bias,
               const double* enh, const uint8_t* wb, const uint8_t* gamma, uint8_t* out) {
-  ChainTables t = make_tables(wb, gamma);
+  const std::vector<uint8_t> blob = make_blob(enh, (stages & ST_GAMMA) ? gamma : nullptr);
+  float wbf[768];
+  bool g_identity = true;
+  for (int i = 0; i < 768; ++i) wbf[i] = (float)wb[i];
+  for (int i = 0; i < 256; ++i) g_identity = g_identity && wb[256 + i] == i;
+  const ChainTables t = chain_tables_from_blob(blob.data(), wbf);
   ChainConsts k;
   memcpy(k.cc, cc, sizeof k.cc); memcpy(k.cc_bias, bias, sizeof k.cc_bias);
-  uint8_t enh_lut[768];
-  for (int c = 0; c < 3; ++c)
-    for (int x = 0; x < 256; ++x) enh_lut[256 * c + x] = enh_gain_lut_entry(x, enh[c]);
-  t.enh = enh_lut;
+  k.cc_has_bias = 0;
+  for (int j = 0; j < 3; ++j) { uint32_t bits; memcpy(&bits, &k.cc_bias[j], 4); if (bits) k.cc_has_bias = 1; }
+  k.wb_g_identity = g_identity ? 1 : 0;
   for (long i = 0; i < n; ++i) {
-    int b = in[3 * i], g = in[3 * i + 1], r = in[3 * i + 2];
+    const int b = in[3 * i], g = in[3 * i + 1], r = in[3 * i + 2];
     const float m = mask ? mask[i] : 1.0f;
-    if (stages & ST_WB) { b = t.wb[b]; g = t.wb[256 + g]; r = t.wb[512 + r]; }
-    if (stages & ST_CC) color_calibrate(b, g, r, k);
-    if (stages & ST_GAMMA) { b = t.gamma[b]; g = t.gamma[g]; r = t.gamma[r]; }
-    if (stages & ST_VIG) vignetting(b, g, r, m, t);
-    if (stages & ST_ENH) enhance(b, g, r, (int)(i % width) >= (width & ~31), t);
-    out[3 * i] = b; out[3 * i + 1] = g; out[3 * i + 2] = r;
+    const bool tail = (int)(i % width) >= (width & ~31);
+    uint32_t p;
+    switch (stages & ST_ALL) {
+#define RIP_CASE(S) case S: p = chain_pixel<S>(b, g, r, m, tail, k, t); break;
+      RIP_CASE(0) RIP_CASE(1) RIP_CASE(2) RIP_CASE(3) RIP_CASE(4) RIP_CASE(5) RIP_CASE(6) RIP_CASE(7)
+      RIP_CASE(8) RIP_CASE(9) RIP_CASE(10) RIP_CASE(11) RIP_CASE(12) RIP_CASE(13) RIP_CASE(14) RIP_CASE(15)
+      RIP_CASE(16) RIP_CASE(17) RIP_CASE(18) RIP_CASE(19) RIP_CASE(20) RIP_CASE(21) RIP_CASE(22) RIP_CASE(23)
+      RIP_CASE(24) RIP_CASE(25) RIP_CASE(26) RIP_CASE(27) RIP_CASE(28) RIP_CASE(29) RIP_CASE(30) RIP_CASE(31)
+#undef RIP_CASE
+      default: p = 0;
+    }
+    out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
   }
 }
 
-// mode 0: demosaic_at everywhere; mode 1: demosaic_quad where legal (the kernels' fast path)
+// mode 0: demosaic_at everywhere; mode 1: demosaic_quad where legal; mode 2: demosaic_quad_swar where legal
 void hs_demosaic(const uint8_t* raw, int rows, int cols, int cfa, int angle, int mode, uint8_t* out) {
   const int orows = (angle == 90 || angle == 270) ? cols : rows;
   const int ocols = (angle == 90 || angle == 270) ? rows : cols;
@@ -79,16 +107,22 @@ void hs_demosaic(const uint8_t* raw, int rows, int cols, int cfa, int angle, int
       int iy, ix; flip_source(angle, rows, cols, oy, ox, iy, ix);
       int b, g, r;
       const int x4 = ix & ~3;
-      if (mode == 1 && x4 >= 4 && x4 + 7 < cols && x4 + 3 <= cols - 2) {
+      if (mode >= 1 && x4 >= 4 && x4 + 7 < cols && x4 + 3 <= cols - 2) {
         int yc = iy < 1 ? 1 : (iy > rows - 2 ? rows - 2 : iy);
         uint32_t w[3][3];
         for (int rr = 0; rr < 3; ++rr)
           for (int j = 0; j < 3; ++j) memcpy(&w[rr][j], raw + (size_t)(yc - 1 + rr) * cols + x4 - 4 + 4 * j, 4);
         const bool row_has_r = ((yc & 1) == ((cfa >> 1) & 1));
         const int cpar = row_has_r ? (cfa & 1) : ((cfa & 1) ^ 1);
-        int bb[4], gg[4], rr4[4];
-        demosaic_quad(w, row_has_r, cpar, bb, gg, rr4);
-        b = bb[ix & 3]; g = gg[ix & 3]; r = rr4[ix & 3];
+        if (mode == 2) {
+          uint32_t Bw, Gw, Rw;
+          demosaic_quad_swar(w, row_has_r, cpar, Bw, Gw, Rw);
+          b = (Bw >> (8 * (ix & 3))) & 255; g = (Gw >> (8 * (ix & 3))) & 255; r = (Rw >> (8 * (ix & 3))) & 255;
+        } else {
+          int bb[4], gg[4], rr4[4];
+          demosaic_quad(w, row_has_r, cpar, bb, gg, rr4);
+          b = bb[ix & 3]; g = gg[ix & 3]; r = rr4[ix & 3];
+        }
       } else {
         demosaic_at(raw, rows, cols, cols, iy, ix, cfa, b, g, r);
       }

@@ -136,6 +136,30 @@ def test_config2_full_chain_1080p(oracle_built, dist):
     assert [np.float32(c) for c in coeff] == [cb[0], cb[1], cr[0], cr[1]]
 
 
+@pytest.mark.parametrize("enc", ENCODINGS)
+@pytest.mark.parametrize("flip", [0, 180])
+def test_fast_and_generic_kernels_agree(oracle_built, enc, flip):
+    """Shapes that qualify for the TMA fast path (width % 16 == 0) also run through the generic kernels
+    (debug/force_generic_kernels): both must equal the oracle, incl. frame borders and partial edge tiles."""
+    rows, cols = 70, 208   # partial tiles in both directions, width % 32 != 0 (cv2 row tail inside the fast path)
+    raw = synth.bayer_frame(rows, cols, enc, 99, "U")
+    kw = dict(FULL); kw["flip"] = flip; kw.pop("undistort")
+    p, o = make_pair(rows, cols, **kw)
+    ref, _ = o.apply(raw, enc)
+    assert_same(p.process(raw, enc), ref, f"fast path {enc} flip {flip}")
+    p._set_bool("debug/force_generic_kernels", True)
+    assert_same(p.process(raw, enc), ref, f"generic path {enc} flip {flip}")
+
+
+def test_generic_kernels_full_chain_1080p(oracle_built):
+    rows, cols = 1080, 1920
+    raw = synth.bayer_frame(rows, cols, "bayer_bggr8", 2001, "N")
+    p, o = make_pair(rows, cols, **FULL)
+    p._set_bool("debug/force_generic_kernels", True)
+    ref, _ = o.apply(raw, "bayer_bggr8")
+    assert_same(p.process(raw, "bayer_bggr8"), ref, "generic kernels, config 2")
+
+
 # ---- config 3: 4032x3040 full chain (one frame against the oracle, batch by property) ------------
 def test_config3_full_chain_12mp_one_frame(oracle_built):
     rows, cols = 3040, 4032

@@ -126,7 +126,7 @@ def test_demosaic_and_flip(hostsim, enc, shape, angle):
     raw = rng.integers(0, 256, shape, dtype=np.uint8)
     ref, _ = O.debayer(raw, enc)
     ref = O.flip(ref, angle)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         out = np.empty(ref.shape, np.uint8)
         hostsim.hs_demosaic(P(raw.ctypes.data), shape[0], shape[1], CFA_ID[enc], angle, mode, P(out.ctypes.data))
         assert out.shape == ref.shape

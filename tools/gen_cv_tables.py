@@ -130,7 +130,7 @@ def main():
         return f"static const {ctype} {name}[{len(vals)}] = {{\n  " + ",\n  ".join(lines) + "\n};\n"
 
     with open(OUT, "w") as f:
-        f.write("// GENERATED by tools/gen_cv_tables.py -- do not edit.\n"
+        f.write("// GENERATED by tools/gen_cv_tables.py -- do not edit.\n#pragma once\n"
                 f"// Validated exhaustively (2^24 triples, BGR2Lab / Lab2BGR / BGR2HSV) against cv2 {cv2.__version__}.\n"
                 "// OpenCV 8-bit colour-conversion constants (imgproc color_lab.cpp / color_hsv.cpp).\n")
         f.write(arr("unsigned short", "kSrgbGammaTab", G))
