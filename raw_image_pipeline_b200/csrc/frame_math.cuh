@@ -138,6 +138,48 @@ RIP_HD void remap_pixel(const uint8_t* src, int rows, int cols, size_t pitch, fl
   }
 }
 
+// ---- the same remap from a 4-byte B,G,R,0 source (the fused kernel's intermediate format) ------------
+// One 32-bit load per tap; the bilinear weights factor exactly in integers,
+//   sum w*p = 32 * [ (32-ay) * ((32-ax) p00 + ax p01) + ay * ((32-ax) p10 + ax p11) ],
+// so the horizontal step is a byte dot product (dp4a) and (acc + 2^14) >> 15 == (V + 512) >> 10.
+RIP_HD uint32_t dot4_u8(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __dp4a(a, b, 0u);
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+  return r;
+#endif
+}
+// returns b | g << 8 | r << 16; `pitch_px` = source row pitch in pixels
+RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, size_t pitch_px, float mx, float my) {
+  const int sx = remap_fix(mx), sy = remap_fix(my);
+  const int ix = sx >> 5, iy = sy >> 5;
+  const uint32_t ax = (uint32_t)(sx & 31), ay = (uint32_t)(sy & 31);
+  uint32_t t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+  if ((unsigned)ix < (unsigned)(cols - 1) && (unsigned)iy < (unsigned)(rows - 1)) {  // all four taps inside
+    const uint32_t* p = src + (size_t)iy * pitch_px + ix;
+    t00 = p[0]; t01 = p[1]; t10 = p[pitch_px]; t11 = p[pitch_px + 1];
+  } else {  // BORDER_CONSTANT 0: taps outside the image contribute nothing
+    const bool x0 = (unsigned)ix < (unsigned)cols, x1 = (unsigned)(ix + 1) < (unsigned)cols;
+    const bool y0 = (unsigned)iy < (unsigned)rows, y1 = (unsigned)(iy + 1) < (unsigned)rows;
+    const long long o = (long long)iy * (long long)pitch_px + ix;
+    if (y0 && x0) t00 = src[o];
+    if (y0 && x1) t01 = src[o + 1];
+    if (y1 && x0) t10 = src[o + (long long)pitch_px];
+    if (y1 && x1) t11 = src[o + (long long)pitch_px + 1];
+  }
+  const uint32_t wA = ax * 255u + 32u;  // bytes (32 - ax, ax, 0, 0)
+  const uint32_t wB = wA << 16;         // bytes (0, 0, 32 - ax, ax)
+  const uint32_t bg0 = prmt(t00, t01, 0x5140u), bg1 = prmt(t10, t11, 0x5140u);  // B00 B01 G00 G01
+  const uint32_t r0 = prmt(t00, t01, 0x3362u), r1 = prmt(t10, t11, 0x3362u);    // R00 R01 0 0 (byte 3 of a pixel is 0)
+  const uint32_t by = 32u - ay;
+  const uint32_t vb = by * dot4_u8(bg0, wA) + ay * dot4_u8(bg1, wA) + 512u;
+  const uint32_t vg = by * dot4_u8(bg0, wB) + ay * dot4_u8(bg1, wB) + 512u;
+  const uint32_t vr = by * dot4_u8(r0, wA) + ay * dot4_u8(r1, wA) + 512u;
+  return (vb >> 10) | ((vg >> 10) << 8) | ((vr >> 10) << 16);
+}
+
 // ---- PCA white balance: white_balance.cpp:73-136 ----------------------------
 // stats = { sum_b, sum_b2, sum_r, sum_r2, sum_g, max_b, max_g, max_r } as exact integers.
 // Eigen::Matrix2f inverse (fixed-size closed form, fp32, no FMA) then the per-pixel

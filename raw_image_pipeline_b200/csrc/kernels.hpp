@@ -50,9 +50,12 @@ cudaError_t launch_gain_lut(const float* gains_bgr, float* wbf, int n_frames, cu
 // Fast path (rip_fast.cu): TMA-staged tiles, packed-byte demosaic.  fast_path_ok() looks at the input side
 // (Bayer, width % 16 == 0, no 90/270 rotation, 16-byte aligned), fast_out_ok() at the output buffer.
 bool fast_path_ok(const FrameParams& p);
-bool fast_out_ok(const FrameParams& p);
-cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
+bool fast_out_ok(const FrameParams& p, bool bgrx);
+// bgrx: write 4-byte B,G,R,0 pixels (out_pitch = ocols * 4) -- the intermediate format of launch_remap_bgrx
+cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
+// same remap from a 4-byte-per-pixel B,G,R,0 source (p.pitch = cols * 4) to BGR8
+cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches);
 
 }  // namespace rip

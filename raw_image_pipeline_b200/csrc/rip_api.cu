@@ -268,9 +268,11 @@ int ensure_map(rip_pipeline* p) {
 }
 
 // The pipeline proper, on device memory (raw_image_pipeline.hpp:143-172).
+// `keep_bgr_color`: the caller may later ask for getDistColorImage(), so the pre-undistortion image must exist as BGR8;
+// otherwise (batch entry points without a dist_color buffer) it is kept in the 4-byte format the gather prefers.
 int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8_t* d_in, size_t in_pitch,
                    size_t in_frame_stride, int n, uint8_t* d_out, size_t out_frame_stride, uint8_t* d_color_user,
-                   uint32_t stages_override, bool use_override, cudaStream_t stream) {
+                   uint32_t stages_override, bool use_override, cudaStream_t stream, bool keep_bgr_color = true) {
   const Params& q = p->hs.p;
   uint32_t stages = 0;
   int wb_kind = 0;
@@ -300,7 +302,9 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     if (bits != 0) fp.k.cc_has_bias = 1;  // anything but +0.0f (NaN and -0.0f included) keeps the add
   }
   fp.k.wb_g_identity = 0;
-  const size_t color_frame = (size_t)g.frows * g.fcols * 3;
+  const bool fast_in = !p->force_generic && fast_path_ok(fp);
+  const bool bgrx = undistort && !d_color_user && !keep_bgr_color && fast_in;
+  const size_t color_frame = (size_t)g.frows * g.fcols * (bgrx ? 4 : 3);
   if (undistort) {
     if (d_color_user) { fp.out = d_color_user; }
     else { RIP_CUDA(p, sc.color.reserve(color_frame * n)); fp.out = sc.color.as<uint8_t>(); }
@@ -308,9 +312,8 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   } else {
     fp.out = d_out; fp.out_frame_stride = (long long)out_frame_stride;
   }
-  fp.out_pitch = g.fcols * 3;
+  fp.out_pitch = g.fcols * (bgrx ? 4 : 3);
 
-  const bool fast_in = !p->force_generic && fast_path_ok(fp);
   if (stages & ST_WB) {
     RIP_CUDA(p, sc.wb.reserve((size_t)n * 768 * sizeof(float)));
     fp.wbf = sc.wb.as<float>();
@@ -333,19 +336,21 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     }
   }
   RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
-  if (fast_in && fast_out_ok(fp)) RIP_CUDA(p, launch_fused_fast(stages, fp, p->sm_count, stream, &launches));
+  if (fast_in && fast_out_ok(fp, bgrx)) RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));
+  else if (bgrx) return p->fail(RIP_ERR_CUDA, "internal: 4-byte intermediate needs the fast path");
   else RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
   RIP_CUDA(p, p->span_end(stream));
   if (undistort) {
     RemapParams rp{};
     rp.src = fp.out; rp.src_frame_stride = fp.out_frame_stride;
-    rp.rows = g.frows; rp.cols = g.fcols; rp.pitch = g.fcols * 3;
+    rp.rows = g.frows; rp.cols = g.fcols; rp.pitch = g.fcols * (bgrx ? 4 : 3);
     rp.dst = d_out; rp.dst_frame_stride = (long long)out_frame_stride;
     rp.orows = g.orows; rp.ocols = g.ocols; rp.dpitch = g.ocols * 3;
     rp.n_frames = n;
     rp.map = p->d_map.as<float2>();
     RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_REMAP, stream));
-    RIP_CUDA(p, launch_remap(3, rp, stream, &launches));
+    if (bgrx) RIP_CUDA(p, launch_remap_bgrx(rp, p->sm_count, stream, &launches));
+    else RIP_CUDA(p, launch_remap(3, rp, stream, &launches));
     RIP_CUDA(p, p->span_end(stream));
   }
   p->kernel_launches += launches;
@@ -735,7 +740,7 @@ int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame
   if (in_frame_stride < pitch * rows) return p->fail(RIP_ERR_INVALID_ARGUMENT, "in_frame_stride smaller than a frame");
   if (out_frame_stride < (size_t)g.orows * g.ocols * 3) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
   return process_device(p, p->scratch, g, d_in, pitch, in_frame_stride, n_frames, d_out, out_frame_stride, d_dist_color, 0, false,
-                        static_cast<cudaStream_t>(cuda_stream));
+                        static_cast<cudaStream_t>(cuda_stream), /*keep_bgr_color=*/false);
 }
 
 int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames, int rows, int cols,
@@ -767,7 +772,7 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
     RIP_CUDA(p, cudaMemcpy2DAsync(s.in.ptr, in_frame, in + (size_t)f0 * in_frame_stride, in_frame_stride, in_frame, n,
                                   cudaMemcpyHostToDevice, s.stream));
     rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels, in_frame, n, s.out.as<uint8_t>(), out_frame,
-                        nullptr, 0, false, s.stream);
+                        nullptr, 0, false, s.stream, /*keep_bgr_color=*/false);
     if (rc != RIP_OK) return rc;
     RIP_CUDA(p, cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_frame_stride, s.out.ptr, out_frame, out_frame, n,
                                   cudaMemcpyDeviceToHost, s.stream));

@@ -31,12 +31,14 @@ constexpr int IN_X_WORD0 = 3;           // word holding columns x0-4 .. x0-1
 constexpr int IN_ROWS = TH + 2;         // rows y0-1 .. y0+TH
 constexpr int IN_BYTES = IN_PITCH * IN_ROWS;            // 5440 = what one TMA load delivers
 constexpr int IN_BUF = (IN_BYTES + 127) / 128 * 128;    // 5504
-constexpr int OUT_PITCH = TW * 3;                       // 384
-constexpr int OUT_BUF = OUT_PITCH * TH;                 // 12288
+// output tile: BGR8 (3 B/px, what the caller receives) or BGRX (4 B/px, the intermediate the undistortion
+// gather reads with one 32-bit load per tap)
+template <bool BGRX> struct OutFmt { static constexpr int PITCH = TW * (BGRX ? 4 : 3), BUF = PITCH * TH; };
 
+template <bool BGRX>
 struct FastSmem {
   alignas(128) uint8_t in[2][IN_BUF];
-  alignas(128) uint8_t out[2][OUT_BUF];
+  alignas(128) uint8_t out[2][OutFmt<BGRX>::BUF];
   alignas(16) uint8_t tables[TABLE_BYTES];
   alignas(16) float wbf[768];
   alignas(8) unsigned long long mbar[2];
@@ -125,11 +127,12 @@ __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, i
 // =============================================================================================
 // fused kernel, fast path
 // =============================================================================================
-template <uint32_t STAGES>
+template <uint32_t STAGES, bool BGRX>
 __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map,
                                                    const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+  FastSmem<BGRX>& sm = *reinterpret_cast<FastSmem<BGRX>*>(smem_raw);
+  constexpr int OUT_PITCH = OutFmt<BGRX>::PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
   const long long tiles_per_frame = (long long)tiles_x * tiles_y;
@@ -205,7 +208,10 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
         for (int k = 0; k < 4; ++k)
           px[k] = chain_pixel<STAGES>((Bw >> (8 * k)) & 255, (Gw >> (8 * k)) & 255, (Rw >> (8 * k)) & 255, m[k], false, P.k, T);
       }
-      if (!rev) {
+      if (BGRX) {
+        if (!rev) *reinterpret_cast<uint4*>(s_out + r_in_tile * OUT_PITCH + 16 * lane) = make_uint4(px[0], px[1], px[2], px[3]);
+        else *reinterpret_cast<uint4*>(s_out + (TH - 1 - r_in_tile) * OUT_PITCH + 16 * (31 - lane)) = make_uint4(px[3], px[2], px[1], px[0]);
+      } else if (!rev) {
         uint32_t* o = reinterpret_cast<uint32_t*>(s_out + r_in_tile * OUT_PITCH + 12 * lane);
         o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542);
       } else {  // 180: mirrored inside the tile, pixel order reversed
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
     __syncthreads();
     if (tid == 0) {
       // the TMA unit clips rows/columns beyond the tensor; 4-byte elements
-      tma_store_3d(&out_map, s_out, (c.ox0 * 3) / 4, c.oy0, c.frame);
+      tma_store_3d(&out_map, s_out, BGRX ? c.ox0 : (c.ox0 * 3) / 4, c.oy0, c.frame);
       tma_commit();
     }
   }
@@ -358,24 +364,25 @@ long long total_tiles(const FrameParams& p) {
   return (long long)((p.cols + TW - 1) / TW) * ((p.rows + TH - 1) / TH) * p.n_frames;
 }
 
-template <uint32_t S>
+template <uint32_t S, bool BGRX>
 cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorMap& im, const CUtensorMap& om, int sm_count,
                           cudaStream_t stream) {
   if (stages == S) {
     static int occ = 0;  // per instantiation
+    constexpr size_t smem = sizeof(FastSmem<BGRX>);
     if (occ == 0) {
-      cudaError_t e = cudaFuncSetAttribute(k_fused_fast<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+      cudaError_t e = cudaFuncSetAttribute(k_fused_fast<S, BGRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S>, NT, sizeof(FastSmem));
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S, BGRX>, NT, smem);
       if (e != cudaSuccess) return e;
       if (occ < 1) occ = 1;
     }
     const long long tiles = total_tiles(p), cap = (long long)sm_count * occ;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    k_fused_fast<S><<<grid, NT, sizeof(FastSmem), stream>>>(p, im, om);
+    k_fused_fast<S, BGRX><<<grid, NT, smem, stream>>>(p, im, om);
     return cudaGetLastError();
   }
-  if constexpr (S < ST_ALL) return dispatch_fast<S + 1>(stages, p, im, om, sm_count, stream);
+  if constexpr (S < ST_ALL) return dispatch_fast<S + 1, BGRX>(stages, p, im, om, sm_count, stream);
   return cudaErrorInvalidValue;
 }
 
@@ -389,21 +396,24 @@ bool fast_path_ok(const FrameParams& p) {
   return encode_tiled_fn() != nullptr;
 }
 
-bool fast_out_ok(const FrameParams& p) {
-  if (p.out_pitch != p.ocols * 3 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
+bool fast_out_ok(const FrameParams& p, bool bgrx) {
+  if (p.out_pitch != p.ocols * (bgrx ? 4 : 3) || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0) return false;
   if (p.n_frames > 1 && (p.out_frame_stride % 16 != 0 || p.out_frame_stride <= 0)) return false;
   return true;
 }
 
-cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, int sm_count, cudaStream_t stream, int* launches) {
+cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, int sm_count, cudaStream_t stream, int* launches) {
   CUtensorMap im, om;
   if (!in_map_for(p, &im)) return cudaErrorInvalidValue;
   const cuuint64_t ofs = p.n_frames > 1 ? (cuuint64_t)p.out_frame_stride : (cuuint64_t)p.out_pitch * p.orows;
-  if (!make_map(&om, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.out, (cuuint64_t)(p.ocols * 3 / 4), (cuuint64_t)p.orows, (cuuint64_t)p.n_frames,
-                (cuuint64_t)p.out_pitch, ofs, OUT_PITCH / 4, TH))
+  // the output is described in 4-byte elements: a BGR8 row of `ocols` pixels is ocols * 3 / 4 of them
+  const int pitch_elems = bgrx ? TW : TW * 3 / 4;
+  if (!make_map(&om, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.out, (cuuint64_t)(bgrx ? p.ocols : p.ocols * 3 / 4), (cuuint64_t)p.orows,
+                (cuuint64_t)p.n_frames, (cuuint64_t)p.out_pitch, ofs, pitch_elems, TH))
     return cudaErrorInvalidValue;
   if (launches) ++*launches;
-  return dispatch_fast<0>(stages & ST_ALL, p, im, om, sm_count, stream);
+  return bgrx ? dispatch_fast<0, true>(stages & ST_ALL, p, im, om, sm_count, stream)
+              : dispatch_fast<0, false>(stages & ST_ALL, p, im, om, sm_count, stream);
 }
 
 cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches) {

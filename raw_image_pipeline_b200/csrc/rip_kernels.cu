@@ -408,6 +408,40 @@ __global__ void __launch_bounds__(256) k_remap(const __grid_constant__ RemapPara
   }
 }
 
+// undistortion from the fused kernel's 4-byte intermediate: 4 output pixels per thread, one 32-bit load per tap
+__global__ void __launch_bounds__(256) k_remap_bgrx(const __grid_constant__ RemapParams P) {
+  const int groups_x = (P.ocols + 3) >> 2;
+  const long long per_frame = (long long)groups_x * P.orows;
+  const long long total = per_frame * P.n_frames;
+  const size_t pitch_px = (size_t)P.pitch >> 2;
+  const bool vec_ok = (P.ocols & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.map) | reinterpret_cast<uintptr_t>(P.dst)) & 15) == 0 &&
+                      (P.dst_frame_stride & 3) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int frame = (int)(i / per_frame);
+    const long long rem = i - (long long)frame * per_frame;
+    const int y = (int)(rem / groups_x), x = ((int)(rem - (long long)y * groups_x)) << 2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)frame * P.src_frame_stride);
+    uint8_t* dst = P.dst + (long long)frame * P.dst_frame_stride + (size_t)y * P.dpitch + (size_t)x * 3;
+    const float2* mp = P.map + (size_t)y * P.ocols + x;
+    if (vec_ok) {
+      const float4 m01 = __ldg(reinterpret_cast<const float4*>(mp)), m23 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+      const uint32_t p0 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.x, m01.y);
+      const uint32_t p1 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.z, m01.w);
+      const uint32_t p2 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.x, m23.y);
+      const uint32_t p3 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.z, m23.w);
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+      d[0] = prmt(p0, p1, 0x4210); d[1] = prmt(p1, p2, 0x5421); d[2] = prmt(p2, p3, 0x6542);
+    } else {
+      const int nv = min(4, P.ocols - x);
+      for (int k = 0; k < nv; ++k) {
+        const float2 m = __ldg(mp + k);
+        const uint32_t px = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m.x, m.y);
+        dst[3 * k] = (uint8_t)px; dst[3 * k + 1] = (uint8_t)(px >> 8); dst[3 * k + 2] = (uint8_t)(px >> 16);
+      }
+    }
+  }
+}
+
 // =============================================================================================
 // launchers
 // =============================================================================================
@@ -481,6 +515,17 @@ cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream
   if (channels == 3) k_remap<3><<<(int)blocks, 256, 0, stream>>>(p);
   else if (channels == 1) k_remap<1><<<(int)blocks, 256, 0, stream>>>(p);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches) {
+  const long long total = (long long)((p.ocols + 3) >> 2) * p.orows * p.n_frames;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count * 64;
+  if (blocks > cap) blocks = cap;
+  if (launches) ++*launches;
+  k_remap_bgrx<<<(int)blocks, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -141,6 +141,14 @@ void hs_remap(const uint8_t* src, int rows, int cols, int ch, const float* mx, c
   }
 }
 
+// src: rows x cols B,G,R,0 pixels (uint32)
+void hs_remap_bgrx(const uint32_t* src, int rows, int cols, const float* mx, const float* my, int orows, int ocols, uint8_t* out) {
+  for (long i = 0; i < (long)orows * ocols; ++i) {
+    const uint32_t p = remap_pixel_bgrx(src, rows, cols, (size_t)cols, mx[i], my[i]);
+    out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
+  }
+}
+
 void hs_pca_lut(const unsigned long long* stats, uint8_t* lut_b, uint8_t* lut_r, float* coeff) {
   PcaCoeff c = pca_coefficients(stats);
   coeff[0] = c.alpha_b; coeff[1] = c.beta_b; coeff[2] = c.alpha_r; coeff[3] = c.beta_r;

@@ -153,6 +153,37 @@ def test_remap_random_maps(hostsim, ch):
     assert int((out != ref).sum()) == 0
 
 
+def test_remap_from_bgrx_intermediate_matches_cv2(hostsim):
+    """The 4-byte-per-pixel gather (one load per tap, dp4a horizontal step) is the same function."""
+    rng = np.random.default_rng(77)
+    rows, cols = 97, 131
+    src = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    bgrx = np.zeros((rows, cols, 4), np.uint8); bgrx[..., :3] = src
+    orows, ocols = 120, 152
+    mx = rng.uniform(-3, cols + 2, (orows, ocols)).astype(np.float32)
+    my = rng.uniform(-3, rows + 2, (orows, ocols)).astype(np.float32)
+    mx[0, :10] = np.arange(10); my[0, :10] = 5.0
+    mx[1, :10] = np.arange(10) + 0.5; my[1, :10] = 4.5
+    mx[2, :4] = [1e9, -1e9, np.inf, -np.inf]; my[2, :4] = [3, 3, 3, 3]
+    mx[3, :4] = [cols - 1, cols - 1.0 + 1 / 64, cols - 0.5, -0.984375]; my[3, :4] = [rows - 1, rows - 0.5, 0, -0.5]
+    mx[4, :6] = [cols - 2, cols - 1.5, -1, -0.5, 0, cols - 1]; my[4, :6] = [rows - 2, rows - 1.5, 0, -1, -0.5, rows - 1]
+    ref = cv2.remap(src, mx, my, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    out = np.empty_like(ref)
+    hostsim.hs_remap_bgrx(P(bgrx.ctypes.data), rows, cols, P(mx.ctypes.data), P(my.ctypes.data), orows, ocols, P(out.ctypes.data))
+    assert int((out != ref).sum()) == 0
+    # all 256 x 256 weight combinations on extreme pixel values
+    src2 = rng.choice(np.array([0, 1, 127, 128, 254, 255], np.uint8), (8, 8, 3))
+    b2 = np.zeros((8, 8, 4), np.uint8); b2[..., :3] = src2
+    fx, fy = np.meshgrid(np.arange(32, dtype=np.float32) / 32, np.arange(32, dtype=np.float32) / 32)
+    mx2 = np.tile(fx, (6, 6)) + np.repeat(np.repeat(np.arange(6, dtype=np.float32)[None, :], 6, 0), 32, 0).repeat(32, 1)
+    my2 = np.tile(fy, (6, 6)) + np.repeat(np.repeat(np.arange(6, dtype=np.float32)[:, None], 6, 1), 32, 0).repeat(32, 1)
+    ref2 = cv2.remap(src2, mx2, my2, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    out2 = np.empty_like(ref2)
+    hostsim.hs_remap_bgrx(P(b2.ctypes.data), 8, 8, P(np.ascontiguousarray(mx2).ctypes.data), P(np.ascontiguousarray(my2).ctypes.data),
+                          192, 192, P(out2.ctypes.data))
+    assert int((out2 != ref2).sum()) == 0
+
+
 def test_remap_identity_is_exact():
     """cv::remap with an identity map returns the image (guards the 32768-weight corner)."""
     rng = np.random.default_rng(9)
