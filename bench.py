@@ -57,6 +57,17 @@ def make_pipeline(rows, cols, device=None):
     return p
 
 
+def make_witness_pipeline(device=None):
+    """SURVEY 8d 'HBM-roofline witness': the same fused kernel with only debayer + gamma enabled (BASELINE configs[0]'s
+    module set) -- what the tile machinery sustains when the per-pixel arithmetic is light."""
+    from raw_image_pipeline_b200 import RawImagePipeline
+    p = RawImagePipeline(False, "", "", "", device=device)
+    for name in ("white_balance", "color_calibration", "vignetting_correction", "color_enhancer", "undistortion", "flip"):
+        getattr(p, "set_" + name)(False)
+    p.set_gamma_correction(True); p.set_gamma_correction_method("custom"); p.set_gamma_correction_k(0.8)
+    return p
+
+
 def make_oracle(rows, cols):
     """The reference's CPU path (call-for-call cv2 replay) -- used ONLY as the timed CPU baseline."""
     from oracle import cv2_oracle as O
@@ -241,6 +252,29 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * n * rows * cols * args.steps / (ms_total * 1e-3) / 1e6
 
+    # ---- HBM-roofline witness: debayer + gamma only, same buffers -----------------------------------
+    witness = None
+    if not args.no_witness:
+        pw = make_witness_pipeline(device=local)
+        def step_w():
+            pw.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, ENC, d_out.data_ptr(), host=False, stream=stream)
+        for _ in range(3):
+            step_w()
+        torch.cuda.synchronize()
+        pw._set_bool("profile/kernel_events", True)
+        for _ in range(args.steps):
+            step_w()
+        torch.cuda.synchronize()
+        kw = pw._get_doubles("stats/kernel_ms")
+        pw._set_bool("profile/kernel_events", False)
+        w_ms = kw[2] / max(kw[4 + 2], 1.0)
+        witness = {"modules": "debayer + gamma (k=0.8)", "kernel": "k_fused<gamma, bayer>", "avg_launch_ms": w_ms,
+                   "achieved_gbs": 4.0 * n * rows * cols / (w_ms * 1e-3) / 1e9 if w_ms > 0 else None,
+                   "mpix_per_s": n * rows * cols / (w_ms * 1e-3) / 1e6 if w_ms > 0 else None}
+        del pw
+        step_device()  # leave the full-chain result in d_out for the equality check below
+        torch.cuda.synchronize()
+
     # ---- end to end through the host-buffer entry point (pinned host memory, copies inside) ------
     h_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8).pin_memory()
 
@@ -274,6 +308,22 @@ def run_b200(args):
     algo_bytes = 4.0 * n * rows * cols  # 1 B Bayer read + 3 B BGR8 write per pixel
     achieved = algo_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else 0.0
     step_kernel_ms = {k: kernel_ms[i] / args.steps for i, k in enumerate(["pca_stats", "pca_lut", "fused", "remap"])}
+    def per_launch(i):
+        return kernel_ms[i] / max(kernel_ms[4 + i], 1.0)
+    px = float(n) * rows * cols
+    other = {
+        "k_remap_bgrx": {"algorithmic_bytes_per_px": 14, "avg_launch_ms": per_launch(3),
+                         "achieved_gbs": 14 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None},
+        "k_pca_stats": {"algorithmic_bytes_per_px": 1, "avg_launch_ms": per_launch(0),
+                        "achieved_gbs": px / (per_launch(0) * 1e-3) / 1e9 if per_launch(0) > 0 else None},
+        "whole_step": {"algorithmic_bytes_per_px": 19, "ms": ms_total / args.steps,
+                       "achieved_gbs": 19 * px / (ms_total / args.steps * 1e-3) / 1e9},
+    }
+    for v in other.values():
+        if v.get("achieved_gbs"):
+            v["frac_of_peak"] = v["achieved_gbs"] / peak
+    if witness and witness.get("achieved_gbs"):
+        witness["frac_of_peak"] = witness["achieved_gbs"] / peak
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
@@ -291,7 +341,8 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, bayer>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fused_ms,
-                     "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)"},
+                     "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)",
+                     "other_kernels": other, "witness_debayer_gamma": witness},
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * rows * cols) * world,
                 "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "steps": e2e_steps,
                 "ms_per_step": dt_e2e / max(e2e_steps, 1) * 1e3,
@@ -321,6 +372,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-witness", action="store_true", help="skip the debayer+gamma-only roofline witness")
     ap.add_argument("--e2e-steps", type=int, default=10)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -6,7 +6,7 @@
 //     load of tile i+1 runs under the arithmetic of tile i;
 //   * the demosaic stencil runs on packed bytes (4 px per 32-bit word, frame_math.cuh demosaic_quad_swar);
 //   * the BGR8 tile is assembled in shared memory and leaves through one TMA store per tile
-//     (cp.async.bulk.tensor ... bulk_group), double buffered, clipped to the frame by the hardware;
+//     (cp.async.bulk.tensor ... bulk_group), clipped to the frame by the hardware;
 //   * persistent grid: resident CTAs walk the tile list of the whole batch frame-major.
 //
 // Everything else (ragged widths, unaligned buffers, 90/270 rotations, 3-channel inputs) takes the
@@ -38,7 +38,7 @@ template <bool BGRX> struct OutFmt { static constexpr int PITCH = TW * (BGRX ? 4
 template <bool BGRX>
 struct FastSmem {
   alignas(128) uint8_t in[2][IN_BUF];
-  alignas(128) uint8_t out[2][OutFmt<BGRX>::BUF];
+  alignas(128) uint8_t out[OutFmt<BGRX>::BUF];  // single buffer: the TMA store of tile i has drained long before tile i+1 is assembled
   alignas(16) uint8_t tables[TABLE_BYTES];
   alignas(16) float wbf[768];
   alignas(8) unsigned long long mbar[2];
@@ -171,18 +171,18 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
         mbar_expect_tx(&sm.mbar[buf ^ 1], IN_BYTES);
         tma_load_3d(sm.in[buf ^ 1], &in_map, &sm.mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
       }
-      tma_wait_read<1>();  // the store that read out[buf] two iterations ago has drained
+      tma_wait_read<0>();  // the store of the previous tile has finished reading `out`
     }
     if ((STAGES & ST_WB) && c.frame != cur_frame) {
       const float* src = P.wbf + (size_t)c.frame * 768;
       for (int i = tid; i < 768; i += NT) sm.wbf[i] = src[i];  // plain load: written by a prior kernel
       cur_frame = c.frame;
     }
-    __syncthreads();  // out[buf] reusable, wbf visible
+    __syncthreads();  // `out` reusable, wbf visible
     mbar_wait(&sm.mbar[buf], (uint32_t)(it >> 1) & 1u);
 
     const uint32_t* s_in = reinterpret_cast<const uint32_t*>(sm.in[buf]);
-    uint8_t* s_out = sm.out[buf];
+    uint8_t* s_out = sm.out;
     const int x = c.x0 + 4 * lane;
 #pragma unroll 1
     for (int rr = 0; rr < TH / 8; ++rr) {
@@ -261,13 +261,11 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
   // per-thread partial results of the current frame
   unsigned sb = 0, sr = 0, sg = 0;             // sums of <= 2^? values: flushed per tile (see below)
   unsigned long long sb2 = 0, sr2 = 0;
-  uint32_t mx_b = 0, mx_g = 0, mx_r = 0;       // packed per-byte maxima (two 16-bit lanes x even/odd bytes folded below)
+  uint32_t mx_b = 0, mx_g = 0, mx_r = 0;       // running maxima in two 16-bit lanes (VIMNMX3.U16x2; byte-wise max is emulated)
 
   auto flush = [&](int frame) {
     // fold the packed maxima to scalars, reduce over the warp, one shared atomic per warp, then one global per CTA
-    unsigned mb = max(max(mx_b & 0xffu, (mx_b >> 8) & 0xffu), max((mx_b >> 16) & 0xffu, mx_b >> 24));
-    unsigned mg = max(max(mx_g & 0xffu, (mx_g >> 8) & 0xffu), max((mx_g >> 16) & 0xffu, mx_g >> 24));
-    unsigned mr = max(max(mx_r & 0xffu, (mx_r >> 8) & 0xffu), max((mx_r >> 16) & 0xffu, mx_r >> 24));
+    unsigned mb = max(mx_b & 0xffffu, mx_b >> 16), mg = max(mx_g & 0xffffu, mx_g >> 16), mr = max(mx_r & 0xffffu, mx_r >> 16);
     unsigned long long vb = sb, vr = sr, vg = sg, vb2 = sb2, vr2 = sr2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -315,7 +313,9 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
       quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
       sb = dp4a_u(Bw, 0x01010101u, sb); sr = dp4a_u(Rw, 0x01010101u, sr); sg = dp4a_u(Gw, 0x01010101u, sg);
       tb2 = dp4a_u(Bw, Bw, tb2); tr2 = dp4a_u(Rw, Rw, tr2);
-      mx_b = __vmaxu4(mx_b, Bw); mx_g = __vmaxu4(mx_g, Gw); mx_r = __vmaxu4(mx_r, Rw);
+      mx_b = __vimax3_u16x2(mx_b, lanes16(Bw, 0), lanes16(Bw, 1));
+      mx_g = __vimax3_u16x2(mx_g, lanes16(Gw, 0), lanes16(Gw, 1));
+      mx_r = __vimax3_u16x2(mx_r, lanes16(Rw, 0), lanes16(Rw, 1));
     }
     sb2 += tb2; sr2 += tr2;
     // sb/sr/sg grow by <= 16 * 255 per tile: a CTA walks < 2^20 tiles of one frame, no overflow before the flush
