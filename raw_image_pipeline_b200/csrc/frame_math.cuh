@@ -83,7 +83,7 @@ RIP_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int shift) {  // low 32 bits 
 // per-byte (a + b + 1) >> 1
 RIP_HD uint32_t avg_round_u8x4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1); }
 // bytes (p, p + 2) of w as two 16-bit lanes
-RIP_HD uint32_t lanes16(uint32_t w, int p) { return prmt(w, 0u, p ? 0x4341u : 0x4240u); }
+RIP_HD uint32_t lanes16(uint32_t w, int p) { return prmt(w, 0u, 0x4240u + 0x0101u * (uint32_t)p); }
 
 RIP_HD void demosaic_quad_swar(const uint32_t w[3][3], bool row_has_r, int cpar, uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
   const uint32_t Nc = w[0][1], Mc = w[1][1], Sc = w[2][1];
@@ -93,12 +93,13 @@ RIP_HD void demosaic_quad_swar(const uint32_t w[3][3], bool row_has_r, int cpar,
   const uint32_t H = avg_round_u8x4(Ml, Mr);  // (W + E + 1) >> 1 at every column
   const uint32_t V = avg_round_u8x4(Nc, Sc);  // (N + S + 1) >> 1
   // colour sites (column parity cpar): 4-neighbour sums in 16-bit lanes
-  const uint32_t X = ((lanes16(Nc, cpar) + lanes16(Sc, cpar) + lanes16(Ml, cpar) + lanes16(Mr, cpar) + 0x00020002u) >> 2) & 0x00ff00ffu;
-  const uint32_t D = ((lanes16(Nl, cpar) + lanes16(Nr, cpar) + lanes16(Sl, cpar) + lanes16(Sr, cpar) + 0x00020002u) >> 2) & 0x00ff00ffu;
+  const uint32_t lsel = 0x4240u + 0x0101u * (uint32_t)cpar;  // PRMT selector of lanes16(., cpar), computed once
+  const uint32_t X = ((prmt(Nc, 0u, lsel) + prmt(Sc, 0u, lsel) + prmt(Ml, 0u, lsel) + prmt(Mr, 0u, lsel) + 0x00020002u) >> 2) & 0x00ff00ffu;
+  const uint32_t D = ((prmt(Nl, 0u, lsel) + prmt(Nr, 0u, lsel) + prmt(Sl, 0u, lsel) + prmt(Sr, 0u, lsel) + 0x00020002u) >> 2) & 0x00ff00ffu;
   // merge: at colour sites G = cross, native = raw, opposite = diagonal; at green sites G = raw,
   // the row's colour = horizontal average, the other colour = vertical average
-  const uint32_t sel = cpar ? 0x2604u : 0x7250u;            // lane values at the colour sites, second operand elsewhere
-  const uint32_t site = cpar ? 0xff00ff00u : 0x00ff00ffu;  // byte mask of the colour sites
+  const uint32_t sel = 0x7250u - 0x4c4cu * (uint32_t)cpar;   // 0x7250 / 0x2604: lane values at the colour sites, second operand elsewhere
+  const uint32_t site = 0x00ff00ffu << (8 * cpar);           // byte mask of the colour sites
   Gw = prmt(X, Mc, sel);
   const uint32_t row_colour = (Mc & site) | (H & ~site);
   const uint32_t other_colour = prmt(D, V, sel);
@@ -151,9 +152,8 @@ RIP_HD uint32_t dot4_u8(uint32_t a, uint32_t b) {
   return r;
 #endif
 }
-// returns b | g << 8 | r << 16; `pitch_px` = source row pitch in pixels
-RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, size_t pitch_px, float mx, float my) {
-  const int sx = remap_fix(mx), sy = remap_fix(my);
+// returns b | g << 8 | r << 16; `pitch_px` = source row pitch in pixels; (sx, sy) = cvRound(map * 32)
+RIP_HD uint32_t remap_pixel_bgrx_fix(const uint32_t* src, int rows, int cols, size_t pitch_px, int sx, int sy) {
   const int ix = sx >> 5, iy = sy >> 5;
   const uint32_t ax = (uint32_t)(sx & 31), ay = (uint32_t)(sy & 31);
   uint32_t t00 = 0, t01 = 0, t10 = 0, t11 = 0;
@@ -178,6 +178,29 @@ RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, size_t
   const uint32_t vg = by * dot4_u8(bg0, wB) + ay * dot4_u8(bg1, wB) + 512u;
   const uint32_t vr = by * dot4_u8(r0, wA) + ay * dot4_u8(r1, wA) + 512u;
   return (vb >> 10) | ((vg >> 10) << 8) | ((vr >> 10) << 16);
+}
+RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, size_t pitch_px, float mx, float my) {
+  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, remap_fix(mx), remap_fix(my));
+}
+
+// Packed fixed-point map entry: the 1/32-pixel source coordinate relative to the destination pixel,
+// two int16: lo = sx - 32 * x, hi = sy - 32 * y.  Exactly the integers cv::remap derives from the float maps, at
+// half the bytes.  REMAP_FAR marks "every tap is outside the image" (also used for NaN / infinite map values).
+constexpr int REMAP_FAR = -32768;
+RIP_HD bool remap_pack_entry(float mx, float my, int x, int y, int rows, int cols, uint32_t& packed) {
+  const int sx = remap_fix(mx), sy = remap_fix(my);
+  const int ix = sx >> 5, iy = sy >> 5;
+  const bool any_tap = ix >= -1 && ix < cols && iy >= -1 && iy < rows;  // otherwise the result is 0 whatever the value
+  if (!any_tap) { packed = (uint32_t)(uint16_t)REMAP_FAR | ((uint32_t)(uint16_t)REMAP_FAR << 16); return true; }
+  const int dx = sx - 32 * x, dy = sy - 32 * y;
+  if (dx <= REMAP_FAR || dx > 32767 || dy <= REMAP_FAR || dy > 32767) return false;  // does not fit: keep the float map
+  packed = (uint32_t)(uint16_t)dx | ((uint32_t)(uint16_t)dy << 16);
+  return true;
+}
+RIP_HD uint32_t remap_pixel_bgrx_packed(const uint32_t* src, int rows, int cols, size_t pitch_px, uint32_t packed, int x, int y) {
+  const int dx = (int)(int16_t)(packed & 0xffffu), dy = (int)(int16_t)(packed >> 16);
+  if (dx == REMAP_FAR) return 0u;
+  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, 32 * x + dx, 32 * y + dy);
 }
 
 // ---- PCA white balance: white_balance.cpp:73-136 ----------------------------

@@ -38,6 +38,7 @@ struct RemapParams {
   int orows, ocols, dpitch;
   int n_frames;
   const float2* map;   // orows x ocols (x, y)
+  const uint32_t* pmap;  // optional packed fixed-point map (frame_math.cuh remap_pack_entry), used by launch_remap_bgrx when set
 };
 
 // All launchers enqueue on `stream`, return the CUDA error of the launch, and add the number of

@@ -74,6 +74,7 @@ struct rip_pipeline {
   struct Span { int kind; cudaEvent_t a, b; };
   bool profile = false;
   bool force_generic = false;  // "debug/force_generic_kernels": tests run both kernel families
+  bool force_float_map = false;  // "debug/force_float_map": undistortion reads the fp32 map even where the packed one exists
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
     if (!profile) return cudaSuccess;
@@ -93,6 +94,7 @@ struct rip_pipeline {
   DevBuf d_tables; bool tables_valid = false; ChainTableParams tables_key;
   DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
   DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
+  DevBuf d_pmap; bool pmap_ok = false; int pmap_src_rows = -1, pmap_src_cols = -1; uint64_t pmap_epoch = 0;  // packed fixed-point map
   std::vector<float> h_map;  // host copy (debug / tests)
   CccState ccc;
 
@@ -267,6 +269,29 @@ int ensure_map(rip_pipeline* p) {
   return RIP_OK;
 }
 
+// Packed fixed-point version of the map (4 B/px instead of 8) for a source image of rows x cols; falls back to the
+// float map when a displacement does not fit 16 bits.
+int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
+  if (p->pmap_epoch == p->hs.und_epoch && p->pmap_src_rows == src_rows && p->pmap_src_cols == src_cols) return RIP_OK;
+  build_host_map(p);
+  const int w = p->map_w, h = p->map_h;
+  std::vector<uint32_t> packed((size_t)w * h);
+  bool ok = true;
+  for (int y = 0; y < h && ok; ++y)
+    for (int x = 0; x < w; ++x) {
+      const float* m = &p->h_map[((size_t)y * w + x) * 2];
+      if (!remap_pack_entry(m[0], m[1], x, y, src_rows, src_cols, packed[(size_t)y * w + x])) { ok = false; break; }
+    }
+  p->pmap_ok = ok;
+  if (ok) {
+    RIP_CUDA(p, cudaDeviceSynchronize());
+    RIP_CUDA(p, p->d_pmap.reserve(packed.size() * sizeof(uint32_t)));
+    RIP_CUDA(p, cudaMemcpy(p->d_pmap.ptr, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  p->pmap_epoch = p->hs.und_epoch; p->pmap_src_rows = src_rows; p->pmap_src_cols = src_cols;
+  return RIP_OK;
+}
+
 // The pipeline proper, on device memory (raw_image_pipeline.hpp:143-172).
 // `keep_bgr_color`: the caller may later ask for getDistColorImage(), so the pre-undistortion image must exist as BGR8;
 // otherwise (batch entry points without a dist_color buffer) it is kept in the 4-byte format the gather prefers.
@@ -348,6 +373,12 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     rp.orows = g.orows; rp.ocols = g.ocols; rp.dpitch = g.ocols * 3;
     rp.n_frames = n;
     rp.map = p->d_map.as<float2>();
+    rp.pmap = nullptr;
+    if (bgrx && !p->force_float_map) {
+      int rc = ensure_packed_map(p, g.frows, g.fcols);
+      if (rc != RIP_OK) return rc;
+      if (p->pmap_ok) rp.pmap = p->d_pmap.as<uint32_t>();
+    }
     RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_REMAP, stream));
     if (bgrx) RIP_CUDA(p, launch_remap_bgrx(rp, p->sm_count, stream, &launches));
     else RIP_CUDA(p, launch_remap(3, rp, stream, &launches));
@@ -422,7 +453,7 @@ void rip_destroy(rip_pipeline* p) {
   if (p->cuda_ready) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    p->d_tables.release(); p->d_vig.release(); p->d_map.release();
+    p->d_tables.release(); p->d_vig.release(); p->d_map.release(); p->d_pmap.release();
     p->d_in.release(); p->d_out.release(); p->d_tmp.release(); p->scratch.release();
     ccc_release(p->ccc);
     for (Slot& s : p->slots) {
@@ -453,6 +484,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "debug")) q.debug = v;
   else if (key_is(key, "profile/kernel_events")) p->profile = v;
   else if (key_is(key, "debug/force_generic_kernels")) p->force_generic = v;
+  else if (key_is(key, "debug/force_float_map")) p->force_float_map = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;

@@ -113,14 +113,12 @@ __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, i
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int j = 0; j < 3; ++j) w[a][j] = p[a * IN_WORDS + j];
-  const bool row_has_r = ((yc & 1) == ((cfa >> 1) & 1));
-  const int cpar = row_has_r ? (cfa & 1) : ((cfa & 1) ^ 1);
+  const bool row_has_r = (((yc ^ (cfa >> 1)) & 1) == 0);
+  const int cpar = (cfa ^ (cfa >> 1) ^ yc) & 1;  // == row_has_r ? (cfa & 1) : (cfa & 1) ^ 1
   demosaic_quad_swar(w, row_has_r, cpar, Bw, Gw, Rw);
-  if (x == 0) {  // column 0 <- column 1
-    Bw = prmt(Bw, 0u, 0x3211u); Gw = prmt(Gw, 0u, 0x3211u); Rw = prmt(Rw, 0u, 0x3211u);
-  }
-  if (x + 4 == cols) {  // column W-1 <- column W-2
-    Bw = prmt(Bw, 0u, 0x2210u); Gw = prmt(Gw, 0u, 0x2210u); Rw = prmt(Rw, 0u, 0x2210u);
+  if (x == 0 || x + 4 == cols) {  // frame border columns (two quads per row): column 0 <- column 1, column W-1 <- column W-2
+    const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
+    Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix);
   }
 }
 
@@ -184,11 +182,12 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
     const uint32_t* s_in = reinterpret_cast<const uint32_t*>(sm.in[buf]);
     uint8_t* s_out = sm.out;
     const int x = c.x0 + 4 * lane;
+    const bool x_in = x >= 0 && x < P.cols;
 #pragma unroll 1
-    for (int rr = 0; rr < TH / 8; ++rr) {
+    for (int rr = 0; rr < TH / 8 && x_in; ++rr) {
       const int r_in_tile = warp + 8 * rr;
       const int y = c.y0 + r_in_tile;
-      if (y < 0 || y >= P.rows || x < 0 || x >= P.cols) continue;
+      if ((unsigned)y >= (unsigned)P.rows) continue;
       uint32_t Bw, Gw, Rw;
       quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
       const int oy = rev ? P.rows - 1 - y : y;

@@ -408,36 +408,50 @@ __global__ void __launch_bounds__(256) k_remap(const __grid_constant__ RemapPara
   }
 }
 
-// undistortion from the fused kernel's 4-byte intermediate: 4 output pixels per thread, one 32-bit load per tap
+// undistortion from the fused kernel's 4-byte intermediate: 4 consecutive output pixels per thread (neighbouring
+// pixels share taps, which the L1 serves), one 32-bit load per tap.  A lane-adjacent pixel assignment with a shared-
+// memory exchange for the stores was measured slower (3.05 vs 2.37 ms per 64 x 12 MP).
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_remap_bgrx(const __grid_constant__ RemapParams P) {
-  const int groups_x = (P.ocols + 3) >> 2;
-  const long long per_frame = (long long)groups_x * P.orows;
-  const long long total = per_frame * P.n_frames;
+  // grid: (ceil(ocols / 4 / 256), orows, n_frames) -- no index arithmetic beyond one multiply-add
+  const int x = (blockIdx.x * 256 + threadIdx.x) << 2, y = blockIdx.y, frame = blockIdx.z;
+  if (x >= P.ocols) return;
   const size_t pitch_px = (size_t)P.pitch >> 2;
-  const bool vec_ok = (P.ocols & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.map) | reinterpret_cast<uintptr_t>(P.dst)) & 15) == 0 &&
+  const bool vec_ok = (P.ocols & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(P.map) | reinterpret_cast<uintptr_t>(P.pmap) | reinterpret_cast<uintptr_t>(P.dst)) & 15) == 0 &&
                       (P.dst_frame_stride & 3) == 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int frame = (int)(i / per_frame);
-    const long long rem = i - (long long)frame * per_frame;
-    const int y = (int)(rem / groups_x), x = ((int)(rem - (long long)y * groups_x)) << 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)frame * P.src_frame_stride);
-    uint8_t* dst = P.dst + (long long)frame * P.dst_frame_stride + (size_t)y * P.dpitch + (size_t)x * 3;
-    const float2* mp = P.map + (size_t)y * P.ocols + x;
-    if (vec_ok) {
-      const float4 m01 = __ldg(reinterpret_cast<const float4*>(mp)), m23 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
-      const uint32_t p0 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.x, m01.y);
-      const uint32_t p1 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.z, m01.w);
-      const uint32_t p2 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.x, m23.y);
-      const uint32_t p3 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.z, m23.w);
-      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-      d[0] = prmt(p0, p1, 0x4210); d[1] = prmt(p1, p2, 0x5421); d[2] = prmt(p2, p3, 0x6542);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)frame * P.src_frame_stride);
+  uint8_t* dst = P.dst + (long long)frame * P.dst_frame_stride + (size_t)y * P.dpitch + (size_t)x * 3;
+  const float2* mp = P.map + (size_t)y * P.ocols + x;
+  const uint32_t* pp = P.pmap + (size_t)y * P.ocols + x;
+  if (vec_ok) {
+    uint32_t p0, p1, p2, p3;
+    if (PACKED) {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(pp));
+      p0 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.x, x, y);
+      p1 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.y, x + 1, y);
+      p2 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.z, x + 2, y);
+      p3 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.w, x + 3, y);
     } else {
-      const int nv = min(4, P.ocols - x);
-      for (int k = 0; k < nv; ++k) {
+      const float4 m01 = __ldg(reinterpret_cast<const float4*>(mp)), m23 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+      p0 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.x, m01.y);
+      p1 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.z, m01.w);
+      p2 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.x, m23.y);
+      p3 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.z, m23.w);
+    }
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    d[0] = prmt(p0, p1, 0x4210); d[1] = prmt(p1, p2, 0x5421); d[2] = prmt(p2, p3, 0x6542);
+  } else {
+    const int nv = min(4, P.ocols - x);
+    for (int k = 0; k < nv; ++k) {
+      uint32_t px;
+      if (PACKED) {
+        px = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, __ldg(pp + k), x + k, y);
+      } else {
         const float2 m = __ldg(mp + k);
-        const uint32_t px = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m.x, m.y);
-        dst[3 * k] = (uint8_t)px; dst[3 * k + 1] = (uint8_t)(px >> 8); dst[3 * k + 2] = (uint8_t)(px >> 16);
+        px = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m.x, m.y);
       }
+      dst[3 * k] = (uint8_t)px; dst[3 * k + 1] = (uint8_t)(px >> 8); dst[3 * k + 2] = (uint8_t)(px >> 16);
     }
   }
 }
@@ -519,13 +533,13 @@ cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream
 }
 
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches) {
-  const long long total = (long long)((p.ocols + 3) >> 2) * p.orows * p.n_frames;
-  if (total <= 0) return cudaSuccess;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)sm_count * 64;
-  if (blocks > cap) blocks = cap;
+  (void)sm_count;
+  if (p.ocols <= 0 || p.orows <= 0 || p.n_frames <= 0) return cudaSuccess;
+  if (p.orows > 65535 || p.n_frames > 65535) return cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((((p.ocols + 3) >> 2) + 255) / 256), (unsigned)p.orows, (unsigned)p.n_frames);
   if (launches) ++*launches;
-  k_remap_bgrx<<<(int)blocks, 256, 0, stream>>>(p);
+  if (p.pmap) k_remap_bgrx<true><<<grid, 256, 0, stream>>>(p);
+  else k_remap_bgrx<false><<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -149,6 +149,21 @@ void hs_remap_bgrx(const uint32_t* src, int rows, int cols, const float* mx, con
   }
 }
 
+// packed fixed-point map path; returns 0 when a displacement does not fit (caller falls back to the float map)
+int hs_remap_bgrx_packed(const uint32_t* src, int rows, int cols, const float* mx, const float* my, int orows, int ocols, uint8_t* out) {
+  std::vector<uint32_t> packed((size_t)orows * ocols);
+  for (int y = 0; y < orows; ++y)
+    for (int x = 0; x < ocols; ++x)
+      if (!remap_pack_entry(mx[(size_t)y * ocols + x], my[(size_t)y * ocols + x], x, y, rows, cols, packed[(size_t)y * ocols + x])) return 0;
+  for (int y = 0; y < orows; ++y)
+    for (int x = 0; x < ocols; ++x) {
+      const long i = (long)y * ocols + x;
+      const uint32_t p = remap_pixel_bgrx_packed(src, rows, cols, (size_t)cols, packed[i], x, y);
+      out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
+    }
+  return 1;
+}
+
 void hs_pca_lut(const unsigned long long* stats, uint8_t* lut_b, uint8_t* lut_r, float* coeff) {
   PcaCoeff c = pca_coefficients(stats);
   coeff[0] = c.alpha_b; coeff[1] = c.beta_b; coeff[2] = c.alpha_r; coeff[3] = c.beta_r;

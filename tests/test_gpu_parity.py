@@ -193,6 +193,23 @@ def test_batch_device_equals_per_frame_calls(oracle_built):
     assert_same(got[1], ref, "batch frame 1 vs oracle")
 
 
+def test_undistortion_batch_paths_packed_and_float_map(oracle_built):
+    """Batch entry points keep the pre-undistortion image in the 4-byte intermediate and read the packed
+    fixed-point map; with debug/force_float_map the same gather reads the fp32 map. Both equal the oracle."""
+    rows, cols, n = 540, 720, 3
+    frames = synth.bayer_batch(n, rows, cols, "bayer_rggb8", 4100, "U")
+    for balance, fov in ((0.0, 0.8), (1.0, 1.2)):
+        kw = dict(FULL); kw["undistort"] = (balance, fov)
+        p, o = make_pair(rows, cols, **kw)
+        packed = p.process_batch(frames, "bayer_rggb8")
+        p._set_bool("debug/force_float_map", True)
+        floatmap = p.process_batch(frames, "bayer_rggb8")
+        for i in range(n):
+            ref, _ = o.apply(frames[i], "bayer_rggb8")
+            assert_same(packed[i], ref, f"packed map frame {i} {balance} {fov}")
+            assert_same(floatmap[i], ref, f"float map frame {i} {balance} {fov}")
+
+
 # ---- 3-channel inputs (apply_pipeline.py usage: a bgr8 PNG) ---------------------------------------
 @pytest.mark.parametrize("enc", ["bgr8", "rgb8"])
 def test_colour_input(oracle_built, enc):

@@ -184,6 +184,30 @@ def test_remap_from_bgrx_intermediate_matches_cv2(hostsim):
     assert int((out2 != ref2).sum()) == 0
 
 
+def test_remap_packed_fixed_point_map_matches_cv2(hostsim):
+    """SURVEY 8f-2: the 4-byte packed map (int16 displacements in 1/32 px) gives cv::remap's result exactly;
+    maps whose displacement does not fit are refused (the library then keeps the float map)."""
+    rng = np.random.default_rng(78)
+    rows, cols = 300, 420
+    src = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    bgrx = np.zeros((rows, cols, 4), np.uint8); bgrx[..., :3] = src
+    xs, ys = np.meshgrid(np.arange(cols, dtype=np.float32), np.arange(rows, dtype=np.float32))
+    mx = (xs + rng.uniform(-200, 200, xs.shape)).astype(np.float32)
+    my = (ys + rng.uniform(-150, 150, ys.shape)).astype(np.float32)
+    mx[0, :6] = [np.nan, np.inf, -np.inf, 1e9, -1e9, -1.0]; my[1, :4] = [np.nan, -1.0, rows - 0.5, rows]
+    mx[2, :4] = [-1.03125, -0.96875, cols - 1, cols - 0.03125]
+    mxc, myc = mx.copy(), my.copy()
+    mxc[np.isnan(mxc)] = -1e9; myc[np.isnan(myc)] = -1e9   # what the library uploads (rip_api.cu build_host_map)
+    ref = cv2.remap(src, mxc, myc, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    out = np.empty_like(ref)
+    ok = hostsim.hs_remap_bgrx_packed(P(bgrx.ctypes.data), rows, cols, P(mxc.ctypes.data), P(myc.ctypes.data), rows, cols, P(out.ctypes.data))
+    assert ok == 1 and int((out != ref).sum()) == 0
+    far = mxc.copy(); far[10, 10] = 5.0 + 1100.0   # inside a (hypothetical) wide image but > 1023 px away: must be refused
+    wide = np.zeros((rows, 2000, 4), np.uint8)
+    ok = hostsim.hs_remap_bgrx_packed(P(wide.ctypes.data), rows, 2000, P(far.ctypes.data), P(myc.ctypes.data), rows, cols, P(out.ctypes.data))
+    assert ok == 0
+
+
 def test_remap_identity_is_exact():
     """cv::remap with an identity map returns the image (guards the 32768-weight corner)."""
     rng = np.random.default_rng(9)

@@ -8,7 +8,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 iS, iI, iSm = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
-iW = hdr.index("L1 Wavefronts Shared"); iWi = hdr.index("L1 Wavefronts Shared Ideal")
+iW = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None; iWi = hdr.index("L1 Wavefronts Shared Ideal") if iW is not None else None
 ops, samp = collections.Counter(), collections.Counter(); tot = 0; wf = wfi = 0
 lines = []
 for r in rows[2:]:
@@ -18,7 +18,8 @@ for r in rows[2:]:
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[iS].strip())
     op = m.group(2) if m else r[iS][:8]
     ops[op] += n; tot += n; samp[op] += int(r[iSm] or 0)
-    wf += int(r[iW] or 0); wfi += int(r[iWi] or 0)
+    if iW is not None:
+        wf += int(r[iW] or 0); wfi += int(r[iWi] or 0)
     lines.append((n, int(r[iSm] or 0), r[iS].strip()))
 w = npx / 32
 print(f"total {tot/w:.1f} instr/px; shared wavefronts {wf/w:.1f} per 32 px (ideal {wfi/w:.1f})")
