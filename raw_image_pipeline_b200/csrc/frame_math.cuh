@@ -153,13 +153,14 @@ RIP_HD uint32_t dot4_u8(uint32_t a, uint32_t b) {
 #endif
 }
 // returns b | g << 8 | r << 16; `pitch_px` = source row pitch in pixels; (sx, sy) = cvRound(map * 32)
-RIP_HD uint32_t remap_pixel_bgrx_fix(const uint32_t* src, int rows, int cols, size_t pitch_px, int sx, int sy) {
+RIP_HD uint32_t remap_pixel_bgrx_fix(const uint32_t* src, int rows, int cols, int pitch_px, int sx, int sy) {
   const int ix = sx >> 5, iy = sy >> 5;
   const uint32_t ax = (uint32_t)(sx & 31), ay = (uint32_t)(sy & 31);
   uint32_t t00 = 0, t01 = 0, t10 = 0, t11 = 0;
   if ((unsigned)ix < (unsigned)(cols - 1) && (unsigned)iy < (unsigned)(rows - 1)) {  // all four taps inside
-    const uint32_t* p = src + (size_t)iy * pitch_px + ix;
-    t00 = p[0]; t01 = p[1]; t10 = p[pitch_px]; t11 = p[pitch_px + 1];
+    const uint32_t* p = src + (iy * pitch_px + ix);  // 32-bit pixel index: a frame holds < 2^31 pixels
+    const uint32_t* q = p + pitch_px;
+    t00 = p[0]; t01 = p[1]; t10 = q[0]; t11 = q[1];
   } else {  // BORDER_CONSTANT 0: taps outside the image contribute nothing
     const bool x0 = (unsigned)ix < (unsigned)cols, x1 = (unsigned)(ix + 1) < (unsigned)cols;
     const bool y0 = (unsigned)iy < (unsigned)rows, y1 = (unsigned)(iy + 1) < (unsigned)rows;
@@ -179,7 +180,7 @@ RIP_HD uint32_t remap_pixel_bgrx_fix(const uint32_t* src, int rows, int cols, si
   const uint32_t vr = by * dot4_u8(r0, wA) + ay * dot4_u8(r1, wA) + 512u;
   return (vb >> 10) | ((vg >> 10) << 8) | ((vr >> 10) << 16);
 }
-RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, size_t pitch_px, float mx, float my) {
+RIP_HD uint32_t remap_pixel_bgrx(const uint32_t* src, int rows, int cols, int pitch_px, float mx, float my) {
   return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, remap_fix(mx), remap_fix(my));
 }
 
@@ -197,10 +198,11 @@ RIP_HD bool remap_pack_entry(float mx, float my, int x, int y, int rows, int col
   packed = (uint32_t)(uint16_t)dx | ((uint32_t)(uint16_t)dy << 16);
   return true;
 }
-RIP_HD uint32_t remap_pixel_bgrx_packed(const uint32_t* src, int rows, int cols, size_t pitch_px, uint32_t packed, int x, int y) {
+RIP_HD uint32_t remap_pixel_bgrx_packed(const uint32_t* src, int rows, int cols, int pitch_px, uint32_t packed, int x, int y) {
   const int dx = (int)(int16_t)(packed & 0xffffu), dy = (int)(int16_t)(packed >> 16);
-  if (dx == REMAP_FAR) return 0u;
-  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, 32 * x + dx, 32 * y + dy);
+  // REMAP_FAR -> a coordinate no image contains: every tap fails the bounds tests and the result is 0
+  const int sx = dx == REMAP_FAR ? INT32_MIN : 32 * x + dx;
+  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, sx, 32 * y + dy);
 }
 
 // ---- PCA white balance: white_balance.cpp:73-136 ----------------------------

@@ -250,8 +250,10 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
   if (tid < 8) s_acc[tid] = 0;
   __syncthreads();
   const bool rev = false;  // sums and maxima do not depend on the rotation
-  long long t = blockIdx.x;
-  if (t < total && tid == 0) {
+  // each CTA takes one contiguous run of tiles (at most two frame changes -> at most three flushes)
+  long long t = total * blockIdx.x / gridDim.x;
+  const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  if (t < t_end && tid == 0) {
     const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
     mbar_expect_tx(&mbar[0], IN_BYTES);
     tma_load_3d(s_inb[0], &in_map, &mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
@@ -286,15 +288,15 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
     sb = sr = sg = 0; sb2 = sr2 = 0; mx_b = mx_g = mx_r = 0;
   };
 
-  for (int it = 0; t < total; t += gridDim.x, ++it) {
+  for (int it = 0; t < t_end; ++t, ++it) {
     const int buf = it & 1;
     const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
     if (cur_frame >= 0 && c.frame != cur_frame) flush(cur_frame);  // uniform over the CTA
     cur_frame = c.frame;
     __syncthreads();  // everyone is done reading in[buf ^ 1]
     if (tid == 0) {
-      const long long tn = t + gridDim.x;
-      if (tn < total) {
+      const long long tn = t + 1;
+      if (tn < t_end) {
         const TileCoord cn = tile_coord(tn, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
         mbar_expect_tx(&mbar[buf ^ 1], IN_BYTES);
         tma_load_3d(s_inb[buf ^ 1], &in_map, &mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);

@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(256) k_remap(const __grid_constant__ RemapPara
 // memory exchange for the stores was measured slower (3.05 vs 2.37 ms per 64 x 12 MP).
 template <bool PACKED>
 __global__ void __launch_bounds__(256) k_remap_bgrx(const __grid_constant__ RemapParams P) {
-  // grid: (ceil(ocols / 4 / 256), orows, n_frames) -- no index arithmetic beyond one multiply-add
-  const int x = (blockIdx.x * 256 + threadIdx.x) << 2, y = blockIdx.y, frame = blockIdx.z;
-  if (x >= P.ocols) return;
-  const size_t pitch_px = (size_t)P.pitch >> 2;
+  // a CTA covers 128 x 8 output pixels (warp = one row segment): vertically adjacent outputs share source rows in L1
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) << 2, y = blockIdx.y * 8 + (threadIdx.x >> 5), frame = blockIdx.z;
+  if (x >= P.ocols || y >= P.orows) return;
+  const int pitch_px = P.pitch >> 2;
   const bool vec_ok = (P.ocols & 3) == 0 &&
                       ((reinterpret_cast<uintptr_t>(P.map) | reinterpret_cast<uintptr_t>(P.pmap) | reinterpret_cast<uintptr_t>(P.dst)) & 15) == 0 &&
                       (P.dst_frame_stride & 3) == 0;
@@ -535,8 +535,8 @@ cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches) {
   (void)sm_count;
   if (p.ocols <= 0 || p.orows <= 0 || p.n_frames <= 0) return cudaSuccess;
-  if (p.orows > 65535 || p.n_frames > 65535) return cudaErrorInvalidValue;
-  const dim3 grid((unsigned)((((p.ocols + 3) >> 2) + 255) / 256), (unsigned)p.orows, (unsigned)p.n_frames);
+  if (p.n_frames > 65535) return cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((p.ocols + 127) / 128), (unsigned)((p.orows + 7) / 8), (unsigned)p.n_frames);
   if (launches) ++*launches;
   if (p.pmap) k_remap_bgrx<true><<<grid, 256, 0, stream>>>(p);
   else k_remap_bgrx<false><<<grid, 256, 0, stream>>>(p);

@@ -144,7 +144,7 @@ void hs_remap(const uint8_t* src, int rows, int cols, int ch, const float* mx, c
 // src: rows x cols B,G,R,0 pixels (uint32)
 void hs_remap_bgrx(const uint32_t* src, int rows, int cols, const float* mx, const float* my, int orows, int ocols, uint8_t* out) {
   for (long i = 0; i < (long)orows * ocols; ++i) {
-    const uint32_t p = remap_pixel_bgrx(src, rows, cols, (size_t)cols, mx[i], my[i]);
+    const uint32_t p = remap_pixel_bgrx(src, rows, cols, cols, mx[i], my[i]);
     out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
   }
 }
@@ -158,7 +158,7 @@ int hs_remap_bgrx_packed(const uint32_t* src, int rows, int cols, const float* m
   for (int y = 0; y < orows; ++y)
     for (int x = 0; x < ocols; ++x) {
       const long i = (long)y * ocols + x;
-      const uint32_t p = remap_pixel_bgrx_packed(src, rows, cols, (size_t)cols, packed[i], x, y);
+      const uint32_t p = remap_pixel_bgrx_packed(src, rows, cols, cols, packed[i], x, y);
       out[3 * i] = p & 255; out[3 * i + 1] = (p >> 8) & 255; out[3 * i + 2] = (p >> 16) & 255;
     }
   return 1;

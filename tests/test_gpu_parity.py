@@ -233,3 +233,23 @@ def test_exhaustive_colour_cube_through_the_kernel(oracle_built):
     p, o = make_pair(4096, 4096, cc=True, gamma=0.8, vig=(1.5, 1e-3, 1e-6), enh=(1.0, 1.2, 1.0))
     ref, _ = o.apply(cube, "bgr8")
     assert_same(p.process(cube, "bgr8"), ref, "2^24 cube")
+
+
+def test_batch_device_with_caller_dist_color_buffer(oracle_built):
+    """rip_apply_batch_device's optional `d_dist_color` receives the pre-undistortion BGR8 frames
+    (getDistColorImage of every frame of the batch)."""
+    import torch
+    rows, cols, n = 270, 368, 3
+    frames = synth.bayer_batch(n, rows, cols, "bayer_grbg8", 4200, "N")
+    p, o = make_pair(rows, cols, **FULL)
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8, device="cuda")
+    d_col = torch.empty((n, rows, cols, 3), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    p.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, "bayer_grbg8", d_out.data_ptr(), host=False,
+                        dist_color_ptr=d_col.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(n):
+        ref, _ = o.apply(frames[i], "bayer_grbg8", keep_stages=True)
+        assert_same(d_col[i].cpu().numpy(), o.stages["color_enhancer"], f"dist colour frame {i}")
+        assert_same(d_out[i].cpu().numpy(), ref, f"rect frame {i}")
