@@ -142,6 +142,28 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max((s[2] for s in self.samples), default=None)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: pin this rank's host thread (and, by first touch, its pinned staging buffers) to the NUMA node its
+    GPU hangs off, so that the e2e leg's H2D/D2H traffic of eight ranks does not cross the socket interconnect."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -206,6 +228,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -336,7 +359,7 @@ def run_b200(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "distribution": "N (natural-ish) + sensor cast",
                    "l2": f"inputs {n * rows * cols / 1e6:.0f} MB + outputs {3 * n * rows * cols / 1e6:.0f} MB per step >> 126 MB L2 "
-                         "(no flush needed)", "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                         "(no flush needed)", "parallelism": f"frames sharded over {world} GPU(s), no collective", "host_numa_binding_rank0": numa,
                    "kernel_ms_per_step": step_kernel_ms, "device_equals_host_path": same},
         "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, bayer>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

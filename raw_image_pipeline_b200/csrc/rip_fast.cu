@@ -88,20 +88,35 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // Tiles are enumerated on a grid anchored at the origin of the OUTPUT frame (TMA stores do not take negative
 // coordinates; loads do, with zero fill).  (x0, y0) is the tile's origin in the INPUT frame: equal to the output
 // origin without rotation, mirrored -- and possibly negative for the partial edge tiles -- for 180 degrees.
+// Every CTA walks one contiguous run of the batch's tile list; the position is advanced incrementally (the index
+// divisions would otherwise cost more instructions per tile than the demosaic of a row).
 struct TileCoord {
   int frame, x0, y0, ox0, oy0;
 };
-__device__ __forceinline__ TileCoord tile_coord(long long t, int tiles_x, long long tiles_per_frame, bool rev, int rows, int cols) {
-  TileCoord c;
-  c.frame = (int)(t / tiles_per_frame);
-  const int rem = (int)(t - (long long)c.frame * tiles_per_frame);
-  const int ty = rem / tiles_x;
-  c.ox0 = (rem - ty * tiles_x) * TW;
-  c.oy0 = ty * TH;
-  c.x0 = rev ? cols - c.ox0 - TW : c.ox0;
-  c.y0 = rev ? rows - c.oy0 - TH : c.oy0;
-  return c;
-}
+struct TileIter {
+  int frame, ty, tx;
+  __device__ __forceinline__ void init(long long t, int tiles_x, long long tiles_per_frame) {
+    frame = (int)(t / tiles_per_frame);
+    const int rem = (int)(t - (long long)frame * tiles_per_frame);
+    ty = rem / tiles_x;
+    tx = rem - ty * tiles_x;
+  }
+  __device__ __forceinline__ void advance(int tiles_x, int tiles_y) {
+    if (++tx == tiles_x) {
+      tx = 0;
+      if (++ty == tiles_y) { ty = 0; ++frame; }
+    }
+  }
+  __device__ __forceinline__ TileCoord coord(bool rev, int rows, int cols) const {
+    TileCoord c;
+    c.frame = frame;
+    c.ox0 = tx * TW;
+    c.oy0 = ty * TH;
+    c.x0 = rev ? cols - c.ox0 - TW : c.ox0;
+    c.y0 = rev ? rows - c.oy0 - TH : c.oy0;
+    return c;
+  }
+};
 
 // packed B / G / R words of the four pixels (y, x .. x+3); `s_in` is the staged tile whose row 0 is y0 - 1
 __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, int cols, int cfa, int y0, int y, int x, int lane,
@@ -120,6 +135,47 @@ __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, i
     const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
     Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix);
   }
+}
+
+// ---- vertical sliding window over one 4-pixel column of the staged tile ------------------------------
+// A thread that walks consecutive rows reuses everything a row contributes to its neighbours: per Bayer row the
+// three packed words (centre / shifted left / shifted right) and, in 16-bit lanes, what the rows above and below
+// need from it (A, S) and what it needs from itself (W).  Per output row that leaves 3 shared-memory loads, 2 funnel
+// shifts and 5 byte permutes instead of 9 / 6 / 8 (frame_math.cuh demosaic_quad_swar is the reference form).
+struct BayerRow {
+  uint32_t c, l, r;  // columns x..x+3, x-1..x+2, x+1..x+4
+  uint32_t A;        // centre word, lanes at the colour sites of the rows above / below
+  uint32_t S;        // left + right words, same lanes (their diagonal contribution)
+  uint32_t W;        // left + right words, lanes at this row's own colour sites, + rounding constant
+};
+// `img_row`: row index in the frame (decides the CFA phase); `srow`: row index in the staged tile
+__device__ __forceinline__ BayerRow load_bayer_row(const uint32_t* s_in, int srow, int lane, int img_row, int cfa) {
+  const uint32_t* p = s_in + srow * IN_WORDS + IN_X_WORD0 + lane;
+  const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+  BayerRow b;
+  b.c = w1; b.l = funnel_r(w0, w1, 24); b.r = funnel_r(w1, w2, 8);
+  const uint32_t cpar = (uint32_t)((cfa ^ (cfa >> 1) ^ img_row) & 1);  // column parity of this row's colour sites
+  const uint32_t own = 0x4240u + 0x0101u * cpar, other = 0x4341u - 0x0101u * cpar;
+  b.A = prmt(b.c, 0u, other);
+  b.S = prmt(b.l, 0u, other) + prmt(b.r, 0u, other);
+  b.W = prmt(b.l, 0u, own) + prmt(b.r, 0u, own) + 0x00020002u;
+  return b;
+}
+// packed B / G / R of the row `m` (frame row img_row) between rows `n` (above) and `s` (below)
+__device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRow& m, const BayerRow& s, int img_row, int cfa,
+                                                uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const int cpar = (cfa ^ (cfa >> 1) ^ img_row) & 1;
+  const bool row_has_r = (((img_row ^ (cfa >> 1)) & 1) == 0);
+  const uint32_t H = avg_round_u8x4(m.l, m.r), V = avg_round_u8x4(n.c, s.c);
+  const uint32_t X = ((n.A + s.A + m.W) >> 2) & 0x00ff00ffu;
+  const uint32_t D = ((n.S + s.S + 0x00020002u) >> 2) & 0x00ff00ffu;
+  const uint32_t sel = 0x7250u - 0x4c4cu * (uint32_t)cpar;
+  const uint32_t site = 0x00ff00ffu << (8 * cpar);
+  Gw = prmt(X, m.c, sel);
+  const uint32_t row_colour = (m.c & site) | (H & ~site);
+  const uint32_t other_colour = prmt(D, V, sel);
+  Rw = row_has_r ? row_colour : other_colour;
+  Bw = row_has_r ? other_colour : row_colour;
 }
 
 // =============================================================================================
@@ -150,22 +206,25 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
   __syncthreads();
   const ChainTables T = chain_tables_from_blob(sm.tables, sm.wbf);
 
-  long long t = blockIdx.x;
-  if (t < total && tid == 0) {
-    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+  long long t = total * blockIdx.x / gridDim.x;
+  const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  TileIter ti;
+  ti.init(t, tiles_x, tiles_per_frame);
+  if (t < t_end && tid == 0) {
+    const TileCoord c = ti.coord(rev, P.rows, P.cols);
     mbar_expect_tx(&sm.mbar[0], IN_BYTES);
     tma_load_3d(sm.in[0], &in_map, &sm.mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
   }
   int cur_frame = -1;
   const int tail_start = P.ocols & ~31;  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
 
-  for (int it = 0; t < total; t += gridDim.x, ++it) {
+  for (int it = 0; t < t_end; ++t, ++it) {
     const int buf = it & 1;
-    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    const TileCoord c = ti.coord(rev, P.rows, P.cols);
+    ti.advance(tiles_x, tiles_y);
     if (tid == 0) {
-      const long long tn = t + gridDim.x;
-      if (tn < total) {  // in[buf ^ 1] was last read before the barrier that ended iteration it - 1
-        const TileCoord cn = tile_coord(tn, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+      if (t + 1 < t_end) {  // in[buf ^ 1] was last read before the barrier that ended iteration it - 1
+        const TileCoord cn = ti.coord(rev, P.rows, P.cols);
         mbar_expect_tx(&sm.mbar[buf ^ 1], IN_BYTES);
         tma_load_3d(sm.in[buf ^ 1], &in_map, &sm.mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
       }
@@ -253,8 +312,10 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
   // each CTA takes one contiguous run of tiles (at most two frame changes -> at most three flushes)
   long long t = total * blockIdx.x / gridDim.x;
   const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  TileIter ti;
+  ti.init(t, tiles_x, tiles_per_frame);
   if (t < t_end && tid == 0) {
-    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    const TileCoord c = ti.coord(rev, P.rows, P.cols);
     mbar_expect_tx(&mbar[0], IN_BYTES);
     tma_load_3d(s_inb[0], &in_map, &mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
   }
@@ -290,14 +351,14 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
 
   for (int it = 0; t < t_end; ++t, ++it) {
     const int buf = it & 1;
-    const TileCoord c = tile_coord(t, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+    const TileCoord c = ti.coord(rev, P.rows, P.cols);
+    ti.advance(tiles_x, tiles_y);
     if (cur_frame >= 0 && c.frame != cur_frame) flush(cur_frame);  // uniform over the CTA
     cur_frame = c.frame;
     __syncthreads();  // everyone is done reading in[buf ^ 1]
     if (tid == 0) {
-      const long long tn = t + 1;
-      if (tn < t_end) {
-        const TileCoord cn = tile_coord(tn, tiles_x, tiles_per_frame, rev, P.rows, P.cols);
+      if (t + 1 < t_end) {
+        const TileCoord cn = ti.coord(rev, P.rows, P.cols);
         mbar_expect_tx(&mbar[buf ^ 1], IN_BYTES);
         tma_load_3d(s_inb[buf ^ 1], &in_map, &mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
       }
@@ -305,18 +366,34 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
     mbar_wait(&mbar[buf], (uint32_t)(it >> 1) & 1u);
     const uint32_t* s_in = reinterpret_cast<const uint32_t*>(s_inb[buf]);
     const int x = c.x0 + 4 * lane;
-    unsigned tb2 = 0, tr2 = 0;  // 4 rows x 4 px x 255^2 < 2^21
+    unsigned tb2 = 0, tr2 = 0;  // 4 rows x 4 px x 255^2 x 3 < 2^22
+    // Warp w owns tile rows 4w .. 4w+3.  Frame rows 0 and H-1 are copies of rows 1 and H-2 (OpenCV's border rule), so
+    // only rows 1 .. H-2 are demosaiced and those two count twice (three times when H == 3).
+    const int ya = max(c.y0 + 4 * warp, 1), yb = min(c.y0 + 4 * warp + 3, P.rows - 2);
+    if (x < P.cols && ya <= yb) {
+      BayerRow rn = load_bayer_row(s_in, ya - 1 - c.y0 + 1, lane, ya - 1, P.cfa);
+      BayerRow rm = load_bayer_row(s_in, ya - c.y0 + 1, lane, ya, P.cfa);
 #pragma unroll
-    for (int rr = 0; rr < TH / 8; ++rr) {
-      const int y = c.y0 + warp + 8 * rr;
-      if (y >= P.rows || x >= P.cols) continue;
-      uint32_t Bw, Gw, Rw;
-      quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
-      sb = dp4a_u(Bw, 0x01010101u, sb); sr = dp4a_u(Rw, 0x01010101u, sr); sg = dp4a_u(Gw, 0x01010101u, sg);
-      tb2 = dp4a_u(Bw, Bw, tb2); tr2 = dp4a_u(Rw, Rw, tr2);
-      mx_b = __vimax3_u16x2(mx_b, lanes16(Bw, 0), lanes16(Bw, 1));
-      mx_g = __vimax3_u16x2(mx_g, lanes16(Gw, 0), lanes16(Gw, 1));
-      mx_r = __vimax3_u16x2(mx_r, lanes16(Rw, 0), lanes16(Rw, 1));
+      for (int k = 0; k < 4; ++k) {
+        const int y = ya + k;
+        if (y <= yb) {
+          const BayerRow rs = load_bayer_row(s_in, y + 1 - c.y0 + 1, lane, y + 1, P.cfa);
+          uint32_t Bw, Gw, Rw;
+          demosaic_window(rn, rm, rs, y, P.cfa, Bw, Gw, Rw);
+          if (x == 0 || x + 4 == P.cols) {  // frame border columns: column 0 <- column 1, column W-1 <- column W-2
+            const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
+            Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix);
+          }
+          const uint32_t mult = 1u + (y == 1) + (y == P.rows - 2);
+          const uint32_t ones = 0x01010101u * mult;
+          sb = dp4a_u(Bw, ones, sb); sr = dp4a_u(Rw, ones, sr); sg = dp4a_u(Gw, ones, sg);
+          tb2 += mult * dp4a_u(Bw, Bw, 0u); tr2 += mult * dp4a_u(Rw, Rw, 0u);
+          mx_b = __vimax3_u16x2(mx_b, lanes16(Bw, 0), lanes16(Bw, 1));
+          mx_g = __vimax3_u16x2(mx_g, lanes16(Gw, 0), lanes16(Gw, 1));
+          mx_r = __vimax3_u16x2(mx_r, lanes16(Rw, 0), lanes16(Rw, 1));
+          rn = rm; rm = rs;
+        }
+      }
     }
     sb2 += tb2; sr2 += tr2;
     // sb/sr/sg grow by <= 16 * 255 per tile: a CTA walks < 2^20 tiles of one frame, no overflow before the flush
