@@ -22,15 +22,17 @@ namespace rip {
 
 namespace {
 
-constexpr int TW = 128, TH = 32, NT = 256;
+constexpr int TW = 128, NT = 256;
+constexpr int TH = 32;        // tile height of the fused kernel (occupancy: 3-5 CTAs of ~45-60 KB per SM)
+constexpr int TH_STATS = 128;  // the statistics kernel has no output tile: taller tiles amortise the per-tile work
 // The TMA unit needs the innermost coordinate 16-byte aligned (probed: tools/tma_probe, unaligned x traps with
 // "illegal instruction"), so the 1-pixel halo is fetched as a 16-byte column on each side.
 constexpr int IN_PITCH = 160;           // staged Bayer row: columns x0-16 .. x0+143
 constexpr int IN_WORDS = IN_PITCH / 4;  // 40
 constexpr int IN_X_WORD0 = 3;           // word holding columns x0-4 .. x0-1
-constexpr int IN_ROWS = TH + 2;         // rows y0-1 .. y0+TH
-constexpr int IN_BYTES = IN_PITCH * IN_ROWS;            // 5440 = what one TMA load delivers
-constexpr int IN_BUF = (IN_BYTES + 127) / 128 * 128;    // 5504
+constexpr int IN_BYTES = IN_PITCH * (TH + 2);                  // rows y0-1 .. y0+TH: what one TMA load delivers
+constexpr int IN_BUF = (IN_BYTES + 127) / 128 * 128;
+constexpr int IN_BYTES_STATS = IN_PITCH * (TH_STATS + 2), IN_BUF_STATS = (IN_BYTES_STATS + 127) / 128 * 128;
 // output tile: BGR8 (3 B/px, what the caller receives) or BGRX (4 B/px, the intermediate the undistortion
 // gather reads with one 32-bit load per tap)
 template <bool BGRX> struct OutFmt { static constexpr int PITCH = TW * (BGRX ? 4 : 3), BUF = PITCH * TH; };
@@ -107,13 +109,13 @@ struct TileIter {
       if (++ty == tiles_y) { ty = 0; ++frame; }
     }
   }
-  __device__ __forceinline__ TileCoord coord(bool rev, int rows, int cols) const {
+  __device__ __forceinline__ TileCoord coord(bool rev, int rows, int cols, int th = TH) const {
     TileCoord c;
     c.frame = frame;
     c.ox0 = tx * TW;
-    c.oy0 = ty * TH;
+    c.oy0 = ty * th;
     c.x0 = rev ? cols - c.ox0 - TW : c.ox0;
-    c.y0 = rev ? rows - c.oy0 - TH : c.oy0;
+    c.y0 = rev ? rows - c.oy0 - th : c.oy0;
     return c;
   }
 };
@@ -294,11 +296,11 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
 __device__ __forceinline__ unsigned dp4a_u(uint32_t a, uint32_t b, unsigned c) { return __dp4a(a, b, c); }
 
 __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map) {
-  __shared__ alignas(128) uint8_t s_inb[2][IN_BUF];
+  __shared__ alignas(128) uint8_t s_inb[2][IN_BUF_STATS];
   __shared__ alignas(8) unsigned long long mbar[2];
   __shared__ unsigned long long s_acc[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
+  const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH_STATS - 1) / TH_STATS;
   const long long tiles_per_frame = (long long)tiles_x * tiles_y;
   const long long total = tiles_per_frame * P.n_frames;
   if (tid == 0) {
@@ -315,8 +317,8 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
   TileIter ti;
   ti.init(t, tiles_x, tiles_per_frame);
   if (t < t_end && tid == 0) {
-    const TileCoord c = ti.coord(rev, P.rows, P.cols);
-    mbar_expect_tx(&mbar[0], IN_BYTES);
+    const TileCoord c = ti.coord(rev, P.rows, P.cols, TH_STATS);
+    mbar_expect_tx(&mbar[0], IN_BYTES_STATS);
     tma_load_3d(s_inb[0], &in_map, &mbar[0], c.x0 - 16, c.y0 - 1, c.frame);
   }
   int cur_frame = -1;
@@ -351,30 +353,31 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
 
   for (int it = 0; t < t_end; ++t, ++it) {
     const int buf = it & 1;
-    const TileCoord c = ti.coord(rev, P.rows, P.cols);
+    const TileCoord c = ti.coord(rev, P.rows, P.cols, TH_STATS);
     ti.advance(tiles_x, tiles_y);
     if (cur_frame >= 0 && c.frame != cur_frame) flush(cur_frame);  // uniform over the CTA
     cur_frame = c.frame;
     __syncthreads();  // everyone is done reading in[buf ^ 1]
     if (tid == 0) {
       if (t + 1 < t_end) {
-        const TileCoord cn = ti.coord(rev, P.rows, P.cols);
-        mbar_expect_tx(&mbar[buf ^ 1], IN_BYTES);
+        const TileCoord cn = ti.coord(rev, P.rows, P.cols, TH_STATS);
+        mbar_expect_tx(&mbar[buf ^ 1], IN_BYTES_STATS);
         tma_load_3d(s_inb[buf ^ 1], &in_map, &mbar[buf ^ 1], cn.x0 - 16, cn.y0 - 1, cn.frame);
       }
     }
     mbar_wait(&mbar[buf], (uint32_t)(it >> 1) & 1u);
     const uint32_t* s_in = reinterpret_cast<const uint32_t*>(s_inb[buf]);
     const int x = c.x0 + 4 * lane;
-    unsigned tb2 = 0, tr2 = 0;  // 4 rows x 4 px x 255^2 x 3 < 2^22
-    // Warp w owns tile rows 4w .. 4w+3.  Frame rows 0 and H-1 are copies of rows 1 and H-2 (OpenCV's border rule), so
-    // only rows 1 .. H-2 are demosaiced and those two count twice (three times when H == 3).
-    const int ya = max(c.y0 + 4 * warp, 1), yb = min(c.y0 + 4 * warp + 3, P.rows - 2);
+    unsigned tb2 = 0, tr2 = 0;  // RPW rows x 4 px x 255^2 x 3 < 2^23
+    // Warp w owns RPW consecutive tile rows.  Frame rows 0 and H-1 are copies of rows 1 and H-2 (OpenCV's border rule),
+    // so only rows 1 .. H-2 are demosaiced and those two count twice (three times when H == 3).
+    constexpr int RPW = TH_STATS / 8;
+    const int ya = max(c.y0 + RPW * warp, 1), yb = min(c.y0 + RPW * warp + RPW - 1, P.rows - 2);
     if (x < P.cols && ya <= yb) {
       BayerRow rn = load_bayer_row(s_in, ya - 1 - c.y0 + 1, lane, ya - 1, P.cfa);
       BayerRow rm = load_bayer_row(s_in, ya - c.y0 + 1, lane, ya, P.cfa);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
+#pragma unroll 4
+      for (int k = 0; k < RPW; ++k) {
         const int y = ya + k;
         if (y <= yb) {
           const BayerRow rs = load_bayer_row(s_in, y + 1 - c.y0 + 1, lane, y + 1, P.cfa);
@@ -431,15 +434,15 @@ bool make_map(CUtensorMap* map, CUtensorMapDataType type, const void* base, cuui
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool in_map_for(const FrameParams& p, CUtensorMap* map) {
+bool in_map_for(const FrameParams& p, CUtensorMap* map, int th) {
   // a single frame still needs a legal stride for the (unused) frame dimension
   const cuuint64_t fstride = p.n_frames > 1 ? (cuuint64_t)p.in_frame_stride : (cuuint64_t)p.in_pitch * p.rows;
   return make_map(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, p.in, (cuuint64_t)p.cols, (cuuint64_t)p.rows, (cuuint64_t)p.n_frames,
-                  (cuuint64_t)p.in_pitch, fstride, IN_PITCH, IN_ROWS);
+                  (cuuint64_t)p.in_pitch, fstride, IN_PITCH, th + 2);
 }
 
-long long total_tiles(const FrameParams& p) {
-  return (long long)((p.cols + TW - 1) / TW) * ((p.rows + TH - 1) / TH) * p.n_frames;
+long long total_tiles(const FrameParams& p, int th) {
+  return (long long)((p.cols + TW - 1) / TW) * ((p.rows + th - 1) / th) * p.n_frames;
 }
 
 template <uint32_t S, bool BGRX>
@@ -455,7 +458,7 @@ cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorM
       if (e != cudaSuccess) return e;
       if (occ < 1) occ = 1;
     }
-    const long long tiles = total_tiles(p), cap = (long long)sm_count * occ;
+    const long long tiles = total_tiles(p, TH), cap = (long long)sm_count * occ;
     const int grid = (int)(tiles < cap ? tiles : cap);
     k_fused_fast<S, BGRX><<<grid, NT, smem, stream>>>(p, im, om);
     return cudaGetLastError();
@@ -482,7 +485,7 @@ bool fast_out_ok(const FrameParams& p, bool bgrx) {
 
 cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, int sm_count, cudaStream_t stream, int* launches) {
   CUtensorMap im, om;
-  if (!in_map_for(p, &im)) return cudaErrorInvalidValue;
+  if (!in_map_for(p, &im, TH)) return cudaErrorInvalidValue;
   const cuuint64_t ofs = p.n_frames > 1 ? (cuuint64_t)p.out_frame_stride : (cuuint64_t)p.out_pitch * p.orows;
   // the output is described in 4-byte elements: a BGR8 row of `ocols` pixels is ocols * 3 / 4 of them
   const int pitch_elems = bgrx ? TW : TW * 3 / 4;
@@ -496,7 +499,7 @@ cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, 
 
 cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches) {
   CUtensorMap im;
-  if (!in_map_for(p, &im)) return cudaErrorInvalidValue;
+  if (!in_map_for(p, &im, TH_STATS)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * 8 * p.n_frames, stream);
   if (e != cudaSuccess) return e;
   static int occ = 0;
@@ -505,7 +508,7 @@ cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
   }
-  const long long tiles = total_tiles(p), cap = (long long)sm_count * occ;
+  const long long tiles = total_tiles(p, TH_STATS), cap = (long long)sm_count * occ;
   const int grid = (int)(tiles < cap ? tiles : cap);
   if (launches) ++*launches;
   k_pca_stats_fast<<<grid, NT, 0, stream>>>(p, im);
