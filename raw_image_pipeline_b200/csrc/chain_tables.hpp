@@ -21,10 +21,10 @@ enum : int {
   OFF_YF = 8960,      // u32[256]      LabToYF_b packed (ify << 16) | y
   OFF_SDIV = 9984,    // i32[256]
   OFF_HDIV = 11008,   // i32[256]
-  OFF_HUE = 12032,    // HueEntry[256] enhancer hue gain + HSV2BGR sector/fraction
-  OFF_SF = 14080,     // f32[256]      enhancer saturation gain, * 1/255f
-  OFF_VF = 15104,     // f32[256]      enhancer value gain, * 1/255f
-  TABLE_BYTES = 16128
+  OFF_HUE = 12032,    // HueEntry[288] enhancer hue gain + HSV2BGR sector/fraction, entry j <-> hue j - HUE_BIAS (-32 .. 255)
+  OFF_SF = 14336,     // f32[256]      enhancer saturation gain, * 1/255f
+  OFF_VF = 15360,     // f32[256]      enhancer value gain, * 1/255f
+  TABLE_BYTES = 16384
 };
 
 struct ChainTableParams {
@@ -73,9 +73,12 @@ inline void build_chain_blob(const ChainTableParams& q, uint8_t* blob) {
   HueEntry* hue = reinterpret_cast<HueEntry*>(blob + OFF_HUE);
   float* sf = reinterpret_cast<float*>(blob + OFF_SF);
   float* vf = reinterpret_cast<float*>(blob + OFF_VF);
-  for (int i = 0; i < 256; ++i) {
+  for (int i = 0; i < 256 + HUE_BIAS; ++i) {
+    // hue entry i serves the raw hue i - HUE_BIAS; BGR2HSV wraps negative hues by +180 before the u8 store
+    int h8 = i - HUE_BIAS;
+    if (h8 < 0) h8 += 180;
     // color_enhancer.cpp:42 cv::multiply(hsv, Scalar(hue_gain_, saturation_gain_, value_gain_))
-    const int h = enh_gain_lut_entry(i, q.enh_gain[0]), s = enh_gain_lut_entry(i, q.enh_gain[1]), v = enh_gain_lut_entry(i, q.enh_gain[2]);
+    const int h = enh_gain_lut_entry(h8, q.enh_gain[0]);
     // HSV2RGB_b: h * (6/180f), wrap, sector, fraction (fp32, each operation rounded on its own)
     volatile float hh = (float)h * (6.0f / 180.0f);
     if (hh >= 6.0f) hh = hh - 6.0f;
@@ -83,6 +86,9 @@ inline void build_chain_blob(const ChainTableParams& q, uint8_t* blob) {
     volatile float f = hh - secf;
     hue[i].f = f;
     hue[i].sel = hsv_sector_selector((int)secf);
+  }
+  for (int i = 0; i < 256; ++i) {
+    const int s = enh_gain_lut_entry(i, q.enh_gain[1]), v = enh_gain_lut_entry(i, q.enh_gain[2]);
     volatile float s1 = (float)s * (1.0f / 255.0f), v1 = (float)v * (1.0f / 255.0f);
     sf[i] = s1; vf[i] = v1;
   }

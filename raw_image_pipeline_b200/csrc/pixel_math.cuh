@@ -49,6 +49,8 @@ enum : uint32_t {
   ST_ALL = 31u
 };
 
+constexpr int HUE_BIAS = 32;  // bgr_to_hsv leaves negative hues (-30 .. -1) un-wrapped; the table wraps them
+
 // hue entry of the enhancer: everything HSV2BGR derives from the (gained) 8-bit hue
 struct alignas(8) HueEntry {
   float f;       // fractional part of the sector coordinate
@@ -65,7 +67,7 @@ struct ChainTables {
   const uint8_t* inv_g;    // [4096]  sRGBInvGammaTab_b
   const int32_t* sdiv;     // [256]
   const int32_t* hdiv;     // [256]
-  const HueEntry* hue;     // [256]   indexed by the un-gained hue
+  const HueEntry* hue;     // [288]   indexed by HUE_BIAS + the un-gained, un-wrapped hue (-32 .. 255)
   const float* sf;         // [256]   float(sat_gain_lut[s]) * (1/255f)
   const float* vf;         // [256]   float(val_gain_lut[v]) * (1/255f)
 };
@@ -147,9 +149,11 @@ RIP_HD void color_calibrate_f(float fb, float fg, float fr, const ChainConsts& k
 }
 
 // ---- 8-bit BGR -> Lab: cv::cvtColor(COLOR_BGR2Lab), vignetting_correction.cpp:73 (A.7) --
-// `gt` is sRGBGammaTab_b, optionally with the gamma LUT folded in.  L, a, b are returned WITHOUT
-// the saturate_cast: for every one of the 2^24 8-bit inputs they already lie in [0, 255]
-// (checked exhaustively in tests/test_pixel_math_host.py).
+// `gt` is sRGBGammaTab_b, optionally with the gamma LUT folded in.  L, a, b are returned WITHOUT the saturate_cast:
+// for every one of the 2^24 8-bit inputs they already lie in [0, 255] (checked exhaustively in
+// tests/test_pixel_math_host.py).  (An fp32 evaluation of the dot products -- exact, all integers < 2^24 -- with the
+// index taken by F2I.FLOOR was measured: it trades 8 integer-pipe operations for 5 on the conversion unit and is
+// 0.6 % slower.)
 RIP_HD void bgr_to_lab(int b, int g, int r, const uint16_t* gt, const uint16_t* lab_c, int& L, int& A, int& B) {
   const int R_ = gt[r], G_ = gt[g], B_ = gt[b];
   const int fX = lab_c[(R_ * 1777 + G_ * 1541 + B_ * 778 + 2048) >> 12];
@@ -213,8 +217,7 @@ RIP_HD void bgr_to_hsv(int b, int g, int r, const ChainTables& t, int& h, int& s
   int hh = r - g + 4 * d;            // v == b
   if (vmax == g) hh = b - r + 2 * d;
   if (vmax == r) hh = g - b;         // tested first in OpenCV: highest priority
-  hh = (hh * t.hdiv[d] + 2048) >> 12;
-  h = hh < 0 ? hh + 180 : hh;  // 0..179 for every 8-bit input
+  h = (hh * t.hdiv[d] + 2048) >> 12;  // -30 .. 150; OpenCV adds 180 to negative values: done by the consumer
   v = vmax;
 }
 
@@ -229,7 +232,7 @@ RIP_HD void bgr_to_hsv(int b, int g, int r, const ChainTables& t, int& h, int& s
 // (saturate_cast) [probed exhaustively, cv2 4.13.0: both paths use the fused form 1 - s*f].
 // `row_tail` = this pixel's column >= (width & ~31).  Returns b | g << 8 | r << 16.
 RIP_HD uint32_t hsv_gain_to_bgr(int h, int s, int v, bool row_tail, const ChainTables& t) {
-  const HueEntry he = t.hue[h];
+  const HueEntry he = t.hue[h + HUE_BIAS];  // h may be -30 .. -1 (un-wrapped)
   const float f = he.f, sf = t.sf[s], vf = t.vf[v];
   const float t1 = RIP_FMUL(vf, RIP_FSUB(1.0f, sf));
   const float t2 = RIP_FMUL(vf, RIP_FMA(-sf, f, 1.0f));

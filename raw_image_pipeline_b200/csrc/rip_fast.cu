@@ -262,11 +262,11 @@ __global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ Frame
       if ((STAGES & ST_ENH) && oxb >= tail_start) {  // whole quad lies in cv2's scalar row tail (rare: width % 32 != 0)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          px[k] = chain_pixel<STAGES>((Bw >> (8 * k)) & 255, (Gw >> (8 * k)) & 255, (Rw >> (8 * k)) & 255, m[k], true, P.k, T);
+          px[k] = chain_pixel<STAGES>((int)prmt(Bw, 0u, 0x4440u + k), (int)prmt(Gw, 0u, 0x4440u + k), (int)prmt(Rw, 0u, 0x4440u + k), m[k], true, P.k, T);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          px[k] = chain_pixel<STAGES>((Bw >> (8 * k)) & 255, (Gw >> (8 * k)) & 255, (Rw >> (8 * k)) & 255, m[k], false, P.k, T);
+          px[k] = chain_pixel<STAGES>((int)prmt(Bw, 0u, 0x4440u + k), (int)prmt(Gw, 0u, 0x4440u + k), (int)prmt(Rw, 0u, 0x4440u + k), m[k], false, P.k, T);
       }
       if (BGRX) {
         if (!rev) *reinterpret_cast<uint4*>(s_out + r_in_tile * OUT_PITCH + 16 * lane) = make_uint4(px[0], px[1], px[2], px[3]);

@@ -52,7 +52,7 @@ void hs_bgr2hsv(long n, const uint8_t* in, uint8_t* out) {
   const ChainTables t = chain_tables_from_blob(blob.data(), nullptr);
   for (long i = 0; i < n; ++i) {
     int h, s, v; bgr_to_hsv(in[3 * i], in[3 * i + 1], in[3 * i + 2], t, h, s, v);
-    out[3 * i] = h; out[3 * i + 1] = s; out[3 * i + 2] = v;
+    out[3 * i] = h < 0 ? h + 180 : h; out[3 * i + 1] = s; out[3 * i + 2] = v;  // the wrap the hue table applies
   }
 }
 // `width`: row length of the image the n pixels form (selects OpenCV's scalar row tail)
