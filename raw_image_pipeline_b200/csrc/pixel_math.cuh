@@ -186,7 +186,7 @@ RIP_HD void lab_to_bgr(int L, int A, int B, const ChainTables& t, int& b, int& g
   const int fx = ify + ((A * 268435 + 128) >> 13) - 4194;        // 5 * 53687 = 268435
   const int fz = ify - ((B * 41943 + 16) >> 9) + 10484;          // -(bdiv): -(... - 10485 + 1)
   int x = lab_xz_cubic(fx), z = lab_xz_cubic(fz);
-  if (fx <= 3390 || fz <= 3390) {  // dark pixels only: whole warps skip this in ordinary image regions
+  if ((fx < fz ? fx : fz) <= 3390) {  // dark pixels only: whole warps skip this in ordinary image regions
     if (fx <= 3390) x = lab_xz_linear(fx);
     if (fz <= 3390) z = lab_xz_linear(fz);
   }
