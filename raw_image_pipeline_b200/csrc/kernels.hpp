@@ -8,7 +8,7 @@
 
 namespace rip {
 
-enum : int { SRC_BAYER = 0, SRC_BGR = 1, SRC_RGB = 2 };
+enum : int { SRC_BAYER = 0, SRC_BGR = 1, SRC_RGB = 2, SRC_MONO = 3 };
 
 struct FrameParams {
   const uint8_t* in;          // n_frames x rows x in_pitch
@@ -55,6 +55,9 @@ bool fast_out_ok(const FrameParams& p, bool bgrx);
 // bgrx: write 4-byte B,G,R,0 pixels (out_pitch = ocols * 4) -- the intermediate format of launch_remap_bgrx
 cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
+// 1-channel non-Bayer input (mono8 ...): only flip and the gamma LUT apply (the colour modules skip images that do not
+// have 3 channels: white_balance.hpp:50-52, color_calibration.hpp:47-49, color_enhancer.hpp:38-40)
+cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, int* launches);
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
 // same remap from a 4-byte-per-pixel B,G,R,0 source (p.pitch = cols * 4) to BGR8
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches);

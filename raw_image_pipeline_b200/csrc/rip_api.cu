@@ -171,7 +171,8 @@ int classify_encoding(rip_pipeline* p, const std::string& enc, int channels, int
   for (const char* s : kListed)
     if (enc == s) return p->fail(RIP_ERR_INVALID_ARGUMENT, "Encoding [" + enc + "] is a valid pattern but is not supported!");
   if (channels == 3) { src = SRC_BGR; return RIP_OK; }
-  return p->fail(RIP_ERR_UNSUPPORTED, "1-channel non-Bayer input (encoding [" + enc + "]) is not supported by this library");
+  if (channels == 1) { src = SRC_MONO; return RIP_OK; }  // passes through debayer untouched (debayer.cpp:45-79)
+  return p->fail(RIP_ERR_INVALID_ARGUMENT, "images must have 1 or 3 channels");
 }
 
 int frame_geometry(rip_pipeline* p, int rows, int cols, int channels, const std::string& enc, FrameGeom& g) {
@@ -180,14 +181,14 @@ int frame_geometry(rip_pipeline* p, int rows, int cols, int channels, const std:
   g.rows = rows; g.cols = cols; g.channels = channels;
   int rc = classify_encoding(p, enc, channels, g.src, g.cfa, g.out_encoding);
   if (rc != RIP_OK) return rc;
-  g.color = true;
+  g.color = g.src != SRC_MONO;
   g.angle = 0;
   if (q.flip_enabled && (q.flip_angle == 90 || q.flip_angle == 180 || q.flip_angle == 270)) g.angle = q.flip_angle;
   const bool swap = (g.angle == 90 || g.angle == 270);
   g.frows = swap ? cols : rows;
   g.fcols = swap ? rows : cols;
   g.undistort = q.und_enabled && q.und_available && q.dist_model != "none";
-  g.orows = g.frows; g.ocols = g.fcols; g.ochannels = 3;
+  g.orows = g.frows; g.ocols = g.fcols; g.ochannels = g.color ? 3 : 1;
   if (g.undistort) {
     if (q.dist_w <= 0 || q.dist_h <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "undistortion enabled without an image size");
     g.orows = q.dist_h; g.ocols = q.dist_w;  // cv::remap output has the map's size (undistortion.cpp:216,241)
@@ -211,7 +212,11 @@ int stage_mask(rip_pipeline* p, const FrameGeom& g, uint32_t& stages, int& wb_ki
   }
   if (q.cc_enabled && g.color && q.cc_available) stages |= ST_CC;  // color_calibration.hpp:42-56
   if (q.gamma_enabled) stages |= ST_GAMMA;                          // gamma_correction.hpp:32-43
-  if (q.vig_enabled) stages |= ST_VIG;                              // vignetting_correction.hpp:26-33
+  if (q.vig_enabled) {                                              // vignetting_correction.hpp:26-33
+    if (!g.color)  // the reference's cv::cvtColor(BGR2Lab) throws for a 1-channel image (vignetting_correction.cpp:73)
+      return p->fail(RIP_ERR_INVALID_ARGUMENT, "vignetting correction needs a 3-channel image (cv::cvtColor BGR2Lab rejects 1 channel)");
+    stages |= ST_VIG;
+  }
   if (q.enh_enabled && g.color) stages |= ST_ENH;                   // color_enhancer.hpp:33-43
   return RIP_OK;
 }
@@ -329,7 +334,8 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   fp.k.wb_g_identity = 0;
   const bool fast_in = !p->force_generic && fast_path_ok(fp);
   const bool bgrx = undistort && !d_color_user && !keep_bgr_color && fast_in;
-  const size_t color_frame = (size_t)g.frows * g.fcols * (bgrx ? 4 : 3);
+  const int och = g.color ? 3 : 1;
+  const size_t color_frame = (size_t)g.frows * g.fcols * (bgrx ? 4 : och);
   if (undistort) {
     if (d_color_user) { fp.out = d_color_user; }
     else { RIP_CUDA(p, sc.color.reserve(color_frame * n)); fp.out = sc.color.as<uint8_t>(); }
@@ -337,7 +343,7 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   } else {
     fp.out = d_out; fp.out_frame_stride = (long long)out_frame_stride;
   }
-  fp.out_pitch = g.fcols * (bgrx ? 4 : 3);
+  fp.out_pitch = g.fcols * (bgrx ? 4 : och);
 
   if (stages & ST_WB) {
     RIP_CUDA(p, sc.wb.reserve((size_t)n * 768 * sizeof(float)));
@@ -361,16 +367,17 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     }
   }
   RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
-  if (fast_in && fast_out_ok(fp, bgrx)) RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));
+  if (!g.color) RIP_CUDA(p, launch_mono(fp, (stages & ST_GAMMA) != 0, stream, &launches));
+  else if (fast_in && fast_out_ok(fp, bgrx)) RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));
   else if (bgrx) return p->fail(RIP_ERR_CUDA, "internal: 4-byte intermediate needs the fast path");
   else RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
   RIP_CUDA(p, p->span_end(stream));
   if (undistort) {
     RemapParams rp{};
     rp.src = fp.out; rp.src_frame_stride = fp.out_frame_stride;
-    rp.rows = g.frows; rp.cols = g.fcols; rp.pitch = g.fcols * (bgrx ? 4 : 3);
+    rp.rows = g.frows; rp.cols = g.fcols; rp.pitch = g.fcols * (bgrx ? 4 : och);
     rp.dst = d_out; rp.dst_frame_stride = (long long)out_frame_stride;
-    rp.orows = g.orows; rp.ocols = g.ocols; rp.dpitch = g.ocols * 3;
+    rp.orows = g.orows; rp.ocols = g.ocols; rp.dpitch = g.ocols * och;
     rp.n_frames = n;
     rp.map = p->d_map.as<float2>();
     rp.pmap = nullptr;
@@ -381,7 +388,7 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     }
     RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_REMAP, stream));
     if (bgrx) RIP_CUDA(p, launch_remap_bgrx(rp, p->sm_count, stream, &launches));
-    else RIP_CUDA(p, launch_remap(3, rp, stream, &launches));
+    else RIP_CUDA(p, launch_remap(och, rp, stream, &launches));
     RIP_CUDA(p, p->span_end(stream));
   }
   p->kernel_launches += launches;
@@ -743,7 +750,7 @@ int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity,
   } else if (which == RIP_IMAGE_DIST_DEBAYERED) {
     // FlipModule's snapshot (flip.hpp:36-45): recomputed on demand from the retained input
     r = g.frows; c = g.fcols;
-    const size_t bytes = (size_t)r * c * 3;
+    const size_t bytes = (size_t)r * c * g.ochannels;
     RIP_CUDA(p, p->d_tmp.reserve(bytes));
     const size_t pitch = (((size_t)g.cols * g.channels) + 15) & ~(size_t)15;
     Scratch dummy;
@@ -752,8 +759,8 @@ int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity,
     if (rc != RIP_OK) return rc;
     src = p->d_tmp.as<uint8_t>();
   } else return p->fail(RIP_ERR_INVALID_ARGUMENT, "unknown image id");
-  shape(r, c, 3);
-  const size_t bytes = (size_t)r * c * 3;
+  shape(r, c, g.ochannels);
+  const size_t bytes = (size_t)r * c * g.ochannels;
   if (!out || out_capacity < bytes) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "image buffer too small");
   RIP_CUDA(p, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, p->stream));
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
@@ -770,7 +777,7 @@ int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame
   if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
   const size_t pitch = (size_t)cols * channels;
   if (in_frame_stride < pitch * rows) return p->fail(RIP_ERR_INVALID_ARGUMENT, "in_frame_stride smaller than a frame");
-  if (out_frame_stride < (size_t)g.orows * g.ocols * 3) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
+  if (out_frame_stride < (size_t)g.orows * g.ocols * g.ochannels) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
   return process_device(p, p->scratch, g, d_in, pitch, in_frame_stride, n_frames, d_out, out_frame_stride, d_dist_color, 0, false,
                         static_cast<cudaStream_t>(cuda_stream), /*keep_bgr_color=*/false);
 }
@@ -782,7 +789,7 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
   int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
   if (rc != RIP_OK) return rc;
   if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
-  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * 3;
+  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
   if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
   // chunk so that copies of chunk i+1 / i-1 overlap the kernels of chunk i
   const int kSlots = 3;

@@ -456,6 +456,23 @@ __global__ void __launch_bounds__(256) k_remap_bgrx(const __grid_constant__ Rema
   }
 }
 
+// 1-channel passthrough: out(oy, ox) = gamma[in(flip_source(oy, ox))]
+__global__ void __launch_bounds__(256) k_mono(const __grid_constant__ FrameParams P, int use_gamma) {
+  const long long per_frame = (long long)P.orows * P.ocols;
+  const long long total = per_frame * P.n_frames;
+  const uint8_t* gamma = P.tables + OFF_GAMMA;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int frame = (int)(i / per_frame);
+    const long long rem = i - (long long)frame * per_frame;
+    const int oy = (int)(rem / P.ocols), ox = (int)(rem - (long long)oy * P.ocols);
+    int iy, ix;
+    flip_source(P.angle, P.rows, P.cols, oy, ox, iy, ix);
+    int v = P.in[(long long)frame * P.in_frame_stride + (size_t)iy * P.in_pitch + ix];
+    if (use_gamma) v = __ldg(gamma + v);
+    P.out[(long long)frame * P.out_frame_stride + (size_t)oy * P.out_pitch + ox] = (uint8_t)v;
+  }
+}
+
 // =============================================================================================
 // launchers
 // =============================================================================================
@@ -517,6 +534,16 @@ cudaError_t launch_gain_lut(const float* gains_bgr, float* wbf, int n_frames, cu
   if (n_frames <= 0) return cudaSuccess;
   if (launches) ++*launches;
   k_gain_lut<<<n_frames, 256, 0, stream>>>(gains_bgr, wbf);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, int* launches) {
+  const long long total = (long long)p.orows * p.ocols * p.n_frames;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (launches) ++*launches;
+  k_mono<<<(int)blocks, 256, 0, stream>>>(p, gamma ? 1 : 0);
   return cudaGetLastError();
 }
 

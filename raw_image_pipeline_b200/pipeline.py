@@ -117,6 +117,8 @@ class RawImagePipeline:
         r, c, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._check(self._lib.rip_apply(self._h, img.ctypes.data, rows, cols, ch, img.strides[0], enc, 64,
                                         out.ctypes.data, out.nbytes, ctypes.byref(r), ctypes.byref(c), ctypes.byref(k)))
+        if och == 1:
+            out = out[:, :, 0]  # a 1-channel cv::Mat is a 2-D array (cvnp convention of the reference binding)
         return out, enc.value.decode()
 
     def process(self, image: np.ndarray, encoding: str) -> np.ndarray:
@@ -241,7 +243,7 @@ class RawImagePipeline:
         out = np.empty((r.value, c.value, k.value), np.uint8)
         self._check(self._lib.rip_get_image(self._h, which, out.ctypes.data, out.nbytes, ctypes.byref(r), ctypes.byref(c),
                                             ctypes.byref(k)))
-        return out
+        return out[:, :, 0] if k.value == 1 else out
 
     def get_dist_debayered_image(self): return self._get_image(L.RIP_IMAGE_DIST_DEBAYERED)
     def get_dist_color_image(self): return self._get_image(L.RIP_IMAGE_DIST_COLOR)

@@ -253,3 +253,21 @@ def test_batch_device_with_caller_dist_color_buffer(oracle_built):
         ref, _ = o.apply(frames[i], "bayer_grbg8", keep_stages=True)
         assert_same(d_col[i].cpu().numpy(), o.stages["color_enhancer"], f"dist colour frame {i}")
         assert_same(d_out[i].cpu().numpy(), ref, f"rect frame {i}")
+
+
+@pytest.mark.parametrize("flip", [0, 90, 180])
+def test_mono_input_passes_through_the_colour_modules(oracle_built, flip):
+    """mono8 (1-channel, not Bayer): debayer leaves it alone, white balance / colour calibration / enhancer skip images
+    without 3 channels, flip + gamma LUT + undistortion still apply (SURVEY 8b 'Input kinds')."""
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (270, 362), dtype=np.uint8)
+    p, o = make_pair(270, 362, flip=flip, wb="pca", cc=True, gamma=0.8, enh=(1.0, 1.2, 1.0), undistort=(0.0, 0.8))
+    ref, enc = o.apply(img, "mono8", keep_stages=True)
+    got = p.process(img, "mono8")
+    assert enc == "mono8" and got.ndim == 2
+    assert_same(got, ref, f"mono8 flip {flip}")
+    assert_same(p.get_dist_debayered_image(), o.stages["flip"], "mono debayered+flipped")
+    assert_same(p.get_dist_color_image(), o.stages["color_enhancer"], "mono pre-undistortion")
+    p.set_vignetting_correction(True)
+    with pytest.raises(ValueError):
+        p.process(img, "mono8")
