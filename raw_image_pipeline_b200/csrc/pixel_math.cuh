@@ -75,8 +75,7 @@ struct ChainTables {
 struct ChainConsts {
   float cc[9];      // row-major, channel order B,G,R (Matx33f, color_calibration.cpp:78-79)
   float cc_bias[3];
-  int cc_has_bias;  // 0: all three biases are +0.0 and the add is skipped (y + 0.0f == y up to the sign of zero)
-  int wb_g_identity;  // 1: the G white-balance LUT is the identity (pca), skip the lookup
+  int wb_g_identity;  // 1: the G white-balance LUT is the identity (pca): used by the path without colour calibration
 };
 
 RIP_HD int clamp_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
@@ -141,8 +140,8 @@ RIP_HD void color_calibrate_f(float fb, float fg, float fr, const ChainConsts& k
     float t0 = RIP_FMUL(fb, k.cc[3 * j + 0]);
     float t1 = RIP_FMUL(fg, k.cc[3 * j + 1]);
     float t2 = RIP_FMUL(fr, k.cc[3 * j + 2]);
-    float y = RIP_FADD(RIP_FADD(t0, t1), t2);
-    if (k.cc_has_bias) y = RIP_FADD(y, k.cc_bias[j]);
+    // cv::add with the bias Scalar; a +0.0f bias changes nothing that survives the u8 conversion (-0 -> +0, NaN -> 0)
+    const float y = RIP_FADD(RIP_FADD(RIP_FADD(t0, t1), t2), k.cc_bias[j]);
     o[j] = sat_u8_rint(y);
   }
   b = o[0]; g = o[1]; r = o[2];
@@ -271,8 +270,7 @@ RIP_HD uint32_t chain_pixel(int b, int g, int r, float mask, bool row_tail, cons
   if (STAGES & ST_CC) {
     float fb, fg, fr;
     if (STAGES & ST_WB) {  // white_balance.cpp:117-127 (pca) / ccc.cpp:383-386: per-frame LUTs, kept as floats
-      fb = t.wbf[b]; fr = t.wbf[512 + r];
-      fg = k.wb_g_identity ? u8_to_float(g) : t.wbf[256 + g];
+      fb = t.wbf[b]; fg = t.wbf[256 + g]; fr = t.wbf[512 + r];  // pca: the G table holds the identity
     } else {
       fb = u8_to_float(b); fg = u8_to_float(g); fr = u8_to_float(r);
     }

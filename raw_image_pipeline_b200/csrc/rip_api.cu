@@ -325,12 +325,6 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   fp.vig = p->d_vig.as<float>(); fp.vig_pitch = p->vig_pitch;
   for (int i = 0; i < 9; ++i) fp.k.cc[i] = q.cc_matrix[i];
   for (int i = 0; i < 3; ++i) fp.k.cc_bias[i] = (float)q.cc_bias[i];  // Scalar double -> fp32 on cv::add
-  fp.k.cc_has_bias = 0;
-  for (int i = 0; i < 3; ++i) {
-    uint32_t bits;
-    memcpy(&bits, &fp.k.cc_bias[i], 4);
-    if (bits != 0) fp.k.cc_has_bias = 1;  // anything but +0.0f (NaN and -0.0f included) keeps the add
-  }
   fp.k.wb_g_identity = 0;
   const bool fast_in = !p->force_generic && fast_path_ok(fp);
   const bool bgrx = undistort && !d_color_user && !keep_bgr_color && fast_in;

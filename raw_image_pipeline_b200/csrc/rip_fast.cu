@@ -184,7 +184,7 @@ __device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRo
 // fused kernel, fast path
 // =============================================================================================
 template <uint32_t STAGES, bool BGRX>
-__global__ void __launch_bounds__(NT) k_fused_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map,
+__global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map,
                                                    const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FastSmem<BGRX>& sm = *reinterpret_cast<FastSmem<BGRX>*>(smem_raw);

@@ -77,8 +77,6 @@ void hs_chain(unsigned stages, long n, int width, const uint8_t* in, const float
   const ChainTables t = chain_tables_from_blob(blob.data(), wbf);
   ChainConsts k;
   memcpy(k.cc, cc, sizeof k.cc); memcpy(k.cc_bias, bias, sizeof k.cc_bias);
-  k.cc_has_bias = 0;
-  for (int j = 0; j < 3; ++j) { uint32_t bits; memcpy(&bits, &k.cc_bias[j], 4); if (bits) k.cc_has_bias = 1; }
   k.wb_g_identity = g_identity ? 1 : 0;
   for (long i = 0; i < n; ++i) {
     const int b = in[3 * i], g = in[3 * i + 1], r = in[3 * i + 2];
