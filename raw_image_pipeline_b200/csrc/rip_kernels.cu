@@ -408,50 +408,56 @@ __global__ void __launch_bounds__(256) k_remap(const __grid_constant__ RemapPara
   }
 }
 
-// undistortion from the fused kernel's 4-byte intermediate: 4 consecutive output pixels per thread (neighbouring
-// pixels share taps, which the L1 serves), one 32-bit load per tap.  A lane-adjacent pixel assignment with a shared-
+// undistortion from the fused kernel's 4-byte intermediate: 4 consecutive output pixels per thread and row
+// (neighbouring pixels share taps, which the L1 serves), one 32-bit load per tap.  A lane-adjacent pixel assignment with a shared-
 // memory exchange for the stores was measured slower (3.05 vs 2.37 ms per 64 x 12 MP).
 template <bool PACKED>
 __global__ void __launch_bounds__(256) k_remap_bgrx(const __grid_constant__ RemapParams P) {
-  // a CTA covers 128 x 8 output pixels (warp = one row segment): vertically adjacent outputs share source rows in L1
-  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) << 2, y = blockIdx.y * 8 + (threadIdx.x >> 5), frame = blockIdx.z;
-  if (x >= P.ocols || y >= P.orows) return;
+  // a CTA covers 128 x 64 output pixels: warp w walks rows w, w+8, ... of the tile (the per-thread set-up is
+  // amortised over 32 pixels; vertically adjacent outputs of one CTA share source rows in L1)
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) << 2, frame = blockIdx.z;
+  if (x >= P.ocols) return;
   const int pitch_px = P.pitch >> 2;
   const bool vec_ok = (P.ocols & 3) == 0 &&
                       ((reinterpret_cast<uintptr_t>(P.map) | reinterpret_cast<uintptr_t>(P.pmap) | reinterpret_cast<uintptr_t>(P.dst)) & 15) == 0 &&
                       (P.dst_frame_stride & 3) == 0;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)frame * P.src_frame_stride);
-  uint8_t* dst = P.dst + (long long)frame * P.dst_frame_stride + (size_t)y * P.dpitch + (size_t)x * 3;
-  const float2* mp = P.map + (size_t)y * P.ocols + x;
-  const uint32_t* pp = P.pmap + (size_t)y * P.ocols + x;
-  if (vec_ok) {
-    uint32_t p0, p1, p2, p3;
-    if (PACKED) {
-      const uint4 m = __ldg(reinterpret_cast<const uint4*>(pp));
-      p0 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.x, x, y);
-      p1 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.y, x + 1, y);
-      p2 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.z, x + 2, y);
-      p3 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.w, x + 3, y);
-    } else {
-      const float4 m01 = __ldg(reinterpret_cast<const float4*>(mp)), m23 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
-      p0 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.x, m01.y);
-      p1 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.z, m01.w);
-      p2 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.x, m23.y);
-      p3 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.z, m23.w);
-    }
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    d[0] = prmt(p0, p1, 0x4210); d[1] = prmt(p1, p2, 0x5421); d[2] = prmt(p2, p3, 0x6542);
-  } else {
-    const int nv = min(4, P.ocols - x);
-    for (int k = 0; k < nv; ++k) {
-      uint32_t px;
+  const int y_begin = blockIdx.y * 64 + (threadIdx.x >> 5);
+  const int y_end = min(blockIdx.y * 64 + 64, P.orows);
+  uint8_t* dst = P.dst + (long long)frame * P.dst_frame_stride + (size_t)y_begin * P.dpitch + (size_t)x * 3;
+  size_t moff = (size_t)y_begin * P.ocols + x;
+#pragma unroll 1
+  for (int y = y_begin; y < y_end; y += 8, dst += (size_t)8 * P.dpitch, moff += (size_t)8 * P.ocols) {
+    if (vec_ok) {
+      uint32_t p0, p1, p2, p3;
       if (PACKED) {
-        px = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, __ldg(pp + k), x + k, y);
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(P.pmap + moff));
+        p0 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.x, x, y);
+        p1 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.y, x + 1, y);
+        p2 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.z, x + 2, y);
+        p3 = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, m.w, x + 3, y);
       } else {
-        const float2 m = __ldg(mp + k);
-        px = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m.x, m.y);
+        const float4* mp = reinterpret_cast<const float4*>(P.map + moff);
+        const float4 m01 = __ldg(mp), m23 = __ldg(mp + 1);
+        p0 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.x, m01.y);
+        p1 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m01.z, m01.w);
+        p2 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.x, m23.y);
+        p3 = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m23.z, m23.w);
       }
-      dst[3 * k] = (uint8_t)px; dst[3 * k + 1] = (uint8_t)(px >> 8); dst[3 * k + 2] = (uint8_t)(px >> 16);
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+      d[0] = prmt(p0, p1, 0x4210); d[1] = prmt(p1, p2, 0x5421); d[2] = prmt(p2, p3, 0x6542);
+    } else {
+      const int nv = min(4, P.ocols - x);
+      for (int k = 0; k < nv; ++k) {
+        uint32_t px;
+        if (PACKED) {
+          px = remap_pixel_bgrx_packed(src, P.rows, P.cols, pitch_px, __ldg(P.pmap + moff + k), x + k, y);
+        } else {
+          const float2 m = __ldg(P.map + moff + k);
+          px = remap_pixel_bgrx(src, P.rows, P.cols, pitch_px, m.x, m.y);
+        }
+        dst[3 * k] = (uint8_t)px; dst[3 * k + 1] = (uint8_t)(px >> 8); dst[3 * k + 2] = (uint8_t)(px >> 16);
+      }
     }
   }
 }
@@ -563,7 +569,7 @@ cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t s
   (void)sm_count;
   if (p.ocols <= 0 || p.orows <= 0 || p.n_frames <= 0) return cudaSuccess;
   if (p.n_frames > 65535) return cudaErrorInvalidValue;
-  const dim3 grid((unsigned)((p.ocols + 127) / 128), (unsigned)((p.orows + 7) / 8), (unsigned)p.n_frames);
+  const dim3 grid((unsigned)((p.ocols + 127) / 128), (unsigned)((p.orows + 63) / 64), (unsigned)p.n_frames);
   if (launches) ++*launches;
   if (p.pmap) k_remap_bgrx<true><<<grid, 256, 0, stream>>>(p);
   else k_remap_bgrx<false><<<grid, 256, 0, stream>>>(p);
