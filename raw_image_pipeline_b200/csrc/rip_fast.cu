@@ -449,10 +449,14 @@ template <uint32_t S, bool BGRX>
 cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorMap& im, const CUtensorMap& om, int sm_count,
                           cudaStream_t stream) {
   if (stages == S) {
-    static int occ = 0;  // per instantiation
+    static int occ_of_device[64] = {0};  // per instantiation and device: the shared-memory opt-in is a per-device attribute
     constexpr size_t smem = sizeof(FastSmem<BGRX>);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int& occ = occ_of_device[dev & 63];
     if (occ == 0) {
-      cudaError_t e = cudaFuncSetAttribute(k_fused_fast<S, BGRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(k_fused_fast<S, BGRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S, BGRX>, NT, smem);
       if (e != cudaSuccess) return e;

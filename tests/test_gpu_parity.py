@@ -271,3 +271,34 @@ def test_mono_input_passes_through_the_colour_modules(oracle_built, flip):
     p.set_vignetting_correction(True)
     with pytest.raises(ValueError):
         p.process(img, "mono8")
+
+
+def test_two_gpus_from_one_process(oracle_built):
+    """One pipeline instance per GPU in the same process (rip_set_device): both produce the oracle's bytes,
+    concurrently from two host threads (one host worker per GPU, no collective)."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rows, cols = 540, 720
+    frames = [synth.bayer_frame(rows, cols, "bayer_rggb8", 4300 + i, "N") for i in range(2)]
+    _, o = make_pair(rows, cols, **FULL)
+    refs = [o.apply(f, "bayer_rggb8")[0] for f in frames]
+    got = [None, None]
+
+    def worker(dev):
+        p, _ = make_pair(rows, cols, **FULL)
+        p._check(p._lib.rip_set_device(p._h, dev))
+        for _ in range(3):
+            got[dev] = p.process(frames[dev], "bayer_rggb8")
+        batch = p.process_batch(np.stack([frames[dev]] * 3), "bayer_rggb8")
+        assert_same(batch[2], refs[dev], f"batch on device {dev}")
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for d in range(2):
+        assert got[d] is not None
+        assert_same(got[d], refs[d], f"device {d}")
