@@ -47,3 +47,27 @@ def test_cpp_class_full_chain_on_gpu(cpp_exe, oracle_built, tmp_path):
                         und_fov_scale=0.8)
     ref, _ = O.OraclePipeline(op).apply(raw, "bayer_rggb8")
     assert int(np.count_nonzero(got != ref)) == 0
+
+
+@pytest.fixture(scope="module")
+def cvmat_exe():
+    exe = os.path.join(ROOT, "tests", "cpp", "_test_cpp_api_cvmat")
+    src = os.path.join(ROOT, "tests", "cpp", "test_cpp_api_cvmat.cpp")
+    deps = [src, os.path.join(ROOT, "include", "raw_image_pipeline", "raw_image_pipeline.hpp"),
+            os.path.join(ROOT, "tests", "cpp", "fake_opencv", "opencv2", "core.hpp"), os.path.join(PKG, "librip_b200.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "tests", "cpp", "fake_opencv"),
+                               "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", PKG, "-lrip_b200", "-Wl,-rpath," + PKG])
+    return exe
+
+
+def test_cpp_class_cv_mat_branch_compiles_and_runs_host_side(cvmat_exe):
+    """The `cv::Mat` flavour of the class (what raw_image_pipeline_ros.cpp would see) against a stand-in opencv2/core.hpp."""
+    out = subprocess.run([cvmat_exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), (out.returncode, out.stdout, out.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_class_cv_mat_branch_on_gpu(cvmat_exe):
+    out = subprocess.run([cvmat_exe, "gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), (out.returncode, out.stdout, out.stderr)
