@@ -794,9 +794,12 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
     p->slots.resize(kSlots);
     for (size_t i = old; i < p->slots.size(); ++i) RIP_CUDA(p, cudaStreamCreateWithFlags(&p->slots[i].stream, cudaStreamNonBlocking));
   }
-  // temporal CCC state is a per-stream recurrence: keep chunks in order on the host side
+  // The CCC Kalman tracker is a recurrence over the frames of one camera stream (ccc.cpp:300-340): with temporal
+  // consistency on, all chunks go through one slot so that they execute in order on one CUDA stream.
+  const Params& q = p->hs.p;
+  const int n_slots = (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency) ? 1 : kSlots;
   int slot_i = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, slot_i = (slot_i + 1) % kSlots) {
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, slot_i = (slot_i + 1) % n_slots) {
     const int n = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
     Slot& s = p->slots[slot_i];
     RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again

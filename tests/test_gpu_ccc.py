@@ -119,3 +119,16 @@ def test_config5_4k_full_chain_ccc(oracle_built):
     kw = dict(FULL); kw["wb"] = "ccc"
     p, o = make_pair(rows, cols, **kw)
     check_frame(p, o, raw, "bayer_rggb8", "config5 4K ccc")
+
+
+def test_ccc_temporal_host_batch_spanning_several_chunks(oracle_built):
+    """rip_apply_batch_host splits long batches into chunks on several CUDA streams; the Kalman recurrence must still
+    see the frames in order."""
+    frames = np.stack(sequence() * 3)   # 42 frames -> three chunks of <= 16
+    n, rows, cols = frames.shape
+    p, o = make_pair(rows, cols, wb="ccc", gamma=0.8)
+    p.set_white_balance_temporal_consistency(True); o.p.wb_temporal_consistency = True
+    got = p.process_batch(frames, "bayer_rggb8")
+    for i in range(n):
+        ref, _ = o.apply(frames[i], "bayer_rggb8")
+        assert_same(got[i], ref, f"temporal host batch frame {i}")
