@@ -75,11 +75,14 @@ RIP_API int rip_reset_white_balance_temporal_consistency(rip_pipeline* p);  /* r
 /* ---- keyed setters / getters --------------------------------------------------------------
  * One key per reference setter/getter (raw_image_pipeline.hpp:61-132); keys follow the YAML
  * sections of raw_image_pipeline.cpp:58-159.  See INTEGRATION.md for the full table.
+ * Input kinds (debayer.cpp:45-79): bayer_{rggb,grbg,gbrg,bggr}8 (1 channel -> BGR8), rgb8 / any other 3-channel
+ * encoding (bgr8 ...), and 1-channel non-Bayer images (mono8 ...: only flip, gamma and undistortion apply, like the
+ * reference's modules that skip images without 3 channels; vignetting rejects them).
  *   bool    gpu, debug, <module>/enabled with module in {debayer, flip, white_balance,
  *           color_calibration, gamma_correction, vignetting_correction, color_enhancer,
  *           undistortion}, white_balance/temporal_consistency
  *   int     flip/angle; (get) dist/image_height, dist/image_width, rect/image_height,
- *           rect/image_width, stats/kernel_launches
+ *           rect/image_width, stats/kernel_launches, stats/ccc_u, stats/ccc_v (CCC arg-max of the last rip_apply)
  *   double  white_balance/clipping_percentile, gamma_correction/k, color_enhancer/hue_gain,
  *           color_enhancer/saturation_gain, color_enhancer/value_gain (the reference's
  *           cross-wired setters are reproduced), undistortion/balance, undistortion/fov_scale
@@ -92,7 +95,11 @@ RIP_API int rip_reset_white_balance_temporal_consistency(rip_pipeline* p);  /* r
  *           undistortion/camera_matrix[9], undistortion/distortion_coefficients[4],
  *           undistortion/rectification_matrix[9], undistortion/projection_matrix[12];
  *           (get) dist|rect/camera_matrix[9], /distortion_coefficients[4],
- *           /rectification_matrix[9], /projection_matrix[12]                                 */
+ *           /rectification_matrix[9], /projection_matrix[12]; stats/pca_coefficients[4], stats/ccc_gains[3] (last
+ *           rip_apply), stats/kernel_ms[8] (per-kernel CUDA-event totals and counts since the last query)
+ * Development switches (bool): profile/kernel_events (CUDA events around every kernel launch),
+ *   debug/force_generic_kernels (skip the TMA fast path), debug/force_float_map (undistortion reads the fp32 map
+ *   instead of the packed fixed-point one).  Neither changes a single output byte.                            */
 RIP_API int rip_set_bool(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_int(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_double(rip_pipeline* p, const char* key, double value);
@@ -144,7 +151,8 @@ RIP_API int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_f
  * Host-computed tables exactly as the kernels consume them (no GPU needed): "gamma_lut" (256 B,
  * gamma_correction.cpp:35-42), "enhancer_luts" (768 B), "vignetting_mask" (rows x cols fp32,
  * vignetting_correction.cpp:32-63), "undistortion_map" (dist_h x dist_w interleaved (x, y) fp32,
- * undistortion.cpp:212-220).  `rows`/`cols` are only used by "vignetting_mask".               */
+ * undistortion.cpp:212-220), "ccc_response" (256 x 256 fp64, the convolution part of the last CCC response; needs a
+ * processed frame).  `rows`/`cols` are only used by "vignetting_mask".                                        */
 RIP_API int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void* out, size_t capacity,
                             size_t* bytes);
 
