@@ -250,7 +250,21 @@ __global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ Fr
       const int y = c.y0 + r_in_tile;
       if ((unsigned)y >= (unsigned)P.rows) continue;
       uint32_t Bw, Gw, Rw;
-      quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
+      const int sr = min(max(y, 1), P.rows - 2) - c.y0;  // staged row above the (clamped) centre row
+      if (sr >= 0 && sr + 2 <= TH + 1) {
+        quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
+      } else {
+        // The frame's last row opens a tile (rows % TH == 1), or its first row closes one (same, rotated by 180): the
+        // border rule needs a Bayer row two above / below the tile, outside the staged halo.  One row per frame.
+        const uint8_t* fin = P.in + (long long)c.frame * P.in_frame_stride;
+        Bw = Gw = Rw = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int b, g, r;
+          demosaic_at(fin, P.rows, P.cols, (size_t)P.in_pitch, y, x + k, P.cfa, b, g, r);
+          Bw |= (uint32_t)b << (8 * k); Gw |= (uint32_t)g << (8 * k); Rw |= (uint32_t)r << (8 * k);
+        }
+      }
       const int oy = rev ? P.rows - 1 - y : y;
       const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
       float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};

@@ -1,6 +1,8 @@
 """Randomised differential test on the GPU: seeded random shapes (incl. the smallest legal ones and widths that
 qualify for the TMA fast path), CFA patterns, rotations, stage subsets and parameters -- CUDA path vs the cv2 oracle,
 single frames and small batches, both kernel families."""
+import os
+
 import numpy as np
 import pytest
 
@@ -36,7 +38,7 @@ def random_case(rng):
     return rows, cols, str(rng.choice(ENCODINGS)), str(rng.choice(["U", "N"])), kw
 
 
-@pytest.mark.parametrize("seed", range(100))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RIP_FUZZ_N", "100"))))
 def test_random_configuration(oracle_built, seed):
     rng = np.random.default_rng(9000 + seed)
     rows, cols, enc, dist, kw = random_case(rng)

@@ -302,3 +302,15 @@ def test_two_gpus_from_one_process(oracle_built):
     for d in range(2):
         assert got[d] is not None
         assert_same(got[d], refs[d], f"device {d}")
+
+
+@pytest.mark.parametrize("flip", [0, 180])
+@pytest.mark.parametrize("rows", [33, 65, 97])
+def test_fast_path_when_the_last_frame_row_opens_a_tile(oracle_built, rows, flip):
+    """rows % 32 == 1: the border rule for the frame's last (first, when rotated) row reaches beyond the tile halo."""
+    cols = 48
+    raw = synth.bayer_frame(rows, cols, "bayer_gbrg8", 58, "N")
+    kw = dict(FULL); kw["flip"] = flip; kw.pop("undistort")
+    p, o = make_pair(rows, cols, **kw)
+    ref, _ = o.apply(raw, "bayer_gbrg8")
+    assert_same(p.process(raw, "bayer_gbrg8"), ref, f"rows {rows} flip {flip}")
