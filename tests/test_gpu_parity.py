@@ -314,3 +314,29 @@ def test_fast_path_when_the_last_frame_row_opens_a_tile(oracle_built, rows, flip
     p, o = make_pair(rows, cols, **kw)
     ref, _ = o.apply(raw, "bayer_gbrg8")
     assert_same(p.process(raw, "bayer_gbrg8"), ref, f"rows {rows} flip {flip}")
+
+
+@pytest.mark.parametrize("pad_in,pad_out", [(48, 32), (7, 5)])
+def test_batch_device_with_padded_frame_strides(oracle_built, pad_in, pad_out):
+    """Frames `in_frame_stride` / `out_frame_stride` bytes apart with gaps: 16-byte multiples stay on the TMA fast path,
+    odd gaps fall back to the generic kernels; the gaps are never written."""
+    import torch
+    rows, cols, n = 64, 96, 3
+    frames = synth.bayer_batch(n, rows, cols, "bayer_rggb8", 4400, "U")
+    kw = dict(FULL); kw.pop("undistort")
+    p, o = make_pair(rows, cols, **kw)
+    in_stride, out_stride = rows * cols + pad_in, rows * cols * 3 + pad_out
+    h_in = np.full(n * in_stride, 0xAB, np.uint8)
+    for i in range(n):
+        h_in[i * in_stride:i * in_stride + rows * cols] = frames[i].ravel()
+    d_in = torch.from_numpy(h_in).cuda()
+    d_out = torch.full((n * out_stride,), 0xCD, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    p.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, "bayer_rggb8", d_out.data_ptr(), host=False,
+                        stream=torch.cuda.current_stream().cuda_stream, in_frame_stride=in_stride, out_frame_stride=out_stride)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for i in range(n):
+        ref, _ = o.apply(frames[i], "bayer_rggb8")
+        assert_same(got[i * out_stride:i * out_stride + rows * cols * 3].reshape(rows, cols, 3), ref, f"frame {i}")
+        assert (got[i * out_stride + rows * cols * 3:(i + 1) * out_stride] == 0xCD).all()
