@@ -1,4 +1,6 @@
-// sm_100a kernels of the RAW chain.
+// sm_100a kernels of the RAW chain: the generic family (any shape, rotation, alignment, 1- and 3-channel inputs),
+// the white-balance LUT builders and the undistortion gathers.  The TMA-fed fast family for camera-shaped Bayer frames
+// lives in rip_fast.cu; both run the same per-pixel code (pixel_math.cuh) and produce identical bytes.
 //
 //   k_fused<STAGES>   debayer -> flip -> [WB LUT] -> [colour calibration] -> [gamma LUT] ->
 //                     [Lab vignetting] -> [HSV enhancer] -> BGR8, one pass, everything after the
@@ -7,8 +9,10 @@
 //   k_pca_lut         2x2 solve + per-frame 256-entry LUTs               (white_balance.cpp:105-127)
 //   k_gain_lut        per-frame gain LUTs (ccc)                          (ccc.cpp:383-386)
 //   k_remap<CH>       cv::remap fixed-point bilinear gather               (undistortion.cpp:240-245)
+//   k_remap_bgrx      the same gather from the fast path's 4-byte intermediate, float or packed fixed-point map
+//   k_mono            1-channel non-Bayer passthrough (flip + gamma)
 //
-// Work decomposition: a frame is cut into 128x32-pixel tiles; a persistent grid of 256-thread
+// Work decomposition of k_fused / k_pca_stats: a frame is cut into 128x32-pixel tiles; a persistent grid of 256-thread
 // CTAs walks the tile list of the whole batch (frame-major).  Per tile: stage the Bayer tile
 // (+1 pixel halo, 144 B x 34 rows) in shared memory, each thread demosaics 4 horizontally
 // adjacent pixels per row from three packed 32-bit words per row, runs the chain on them in
