@@ -340,3 +340,18 @@ def test_batch_device_with_padded_frame_strides(oracle_built, pad_in, pad_out):
         ref, _ = o.apply(frames[i], "bayer_rggb8")
         assert_same(got[i * out_stride:i * out_stride + rows * cols * 3].reshape(rows, cols, 3), ref, f"frame {i}")
         assert (got[i * out_stride + rows * cols * 3:(i + 1) * out_stride] == 0xCD).all()
+
+
+def test_strided_input_rows_and_noop_flip_angles(oracle_built):
+    """`step` larger than a row (a cv::Mat ROI / numpy view of a wider buffer), and flip angles the reference ignores
+    (flip.cpp:37-58: anything but 90 / 180 / 270 leaves the image alone even when the module is enabled)."""
+    rows, cols = 70, 112
+    wide = synth.bayer_frame(rows, cols + 40, "bayer_grbg8", 4500, "U")
+    view = wide[:, 8:8 + cols]
+    assert not view.flags.c_contiguous
+    p, o = make_pair(rows, cols, gamma=0.8, enh=(1.0, 1.2, 1.0))
+    ref, _ = o.apply(np.ascontiguousarray(view), "bayer_grbg8")
+    assert_same(p.process(view, "bayer_grbg8"), ref, "strided rows")
+    for angle in (0, 45, 360, -90):
+        p.set_flip(True); p.set_flip_angle(angle)
+        assert_same(p.process(np.ascontiguousarray(view), "bayer_grbg8"), ref, f"flip angle {angle} is a no-op")
