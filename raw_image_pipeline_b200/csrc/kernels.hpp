@@ -24,8 +24,8 @@ struct FrameParams {
   int src;                    // SRC_*
   const uint8_t* tables;      // static blob (TABLE_BYTES)
   const float* wbf;           // n_frames x 3 x 256 per-frame white-balance LUTs (B,G,R) as floats, or null
-  const float* vig;           // vignetting mask, upper half: (orows/2 + 1) x ocols, row qi = |2*oy - orows| >> 1
-  int vig_pitch;              // floats per mask row (== ocols)
+  const float* vig;           // vignetting mask in INPUT-frame coordinates: rows x cols, entry (y, x) = mask at flip_dest(y, x)
+  int vig_pitch;              // floats per mask row (== cols)
   ChainConsts k;
   unsigned long long* stats;  // n_frames x 8 (stats kernel only)
 };

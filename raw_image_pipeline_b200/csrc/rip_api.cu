@@ -92,7 +92,7 @@ struct rip_pipeline {
 
   // device-resident parameters
   DevBuf d_tables; bool tables_valid = false; ChainTableParams tables_key;
-  DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
+  DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_angle = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
   DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
   DevBuf d_pmap; bool pmap_ok = false; int pmap_src_rows = -1, pmap_src_cols = -1; uint64_t pmap_epoch = 0;  // packed fixed-point map
   std::vector<float> h_map;  // host copy (debug / tests)
@@ -236,22 +236,31 @@ int ensure_tables(rip_pipeline* p) {
   return RIP_OK;
 }
 
-int ensure_vignetting(rip_pipeline* p, int rows, int cols) {
+// `rows` x `cols`: the INPUT frame; `angle`: the flip applied after the debayer.  The reference builds the mask for the
+// flipped image; the device copy is stored in input-frame coordinates (entry (y, x) = mask at the output position of
+// input pixel (y, x)), so a thread reads the masks of its four pixels with one aligned 16-byte load whatever the rotation.
+int ensure_vignetting(rip_pipeline* p, int rows, int cols, int angle) {
   const Params& q = p->hs.p;
   const double par[3] = {q.vig_scale, q.vig_a2, q.vig_a4};
-  if (p->vig_rows == rows && p->vig_cols == cols && memcmp(par, p->vig_par, sizeof par) == 0) return RIP_OK;
+  if (p->vig_rows == rows && p->vig_cols == cols && p->vig_angle == angle && memcmp(par, p->vig_par, sizeof par) == 0) return RIP_OK;
+  const bool swap = angle == 90 || angle == 270;
+  const int orows = swap ? cols : rows, ocols = swap ? rows : cols;
   std::vector<float> quad;
   int qr = 0, qc = 0;
-  build_vignetting_quadrant(rows, cols, q.vig_scale, q.vig_a2, q.vig_a4, quad, qr, qc);
-  // device layout: the upper half of the mask at full width, so that four horizontally adjacent pixels
-  // are one aligned 16-byte load; row qi = |2*i - rows| >> 1 serves image rows i and rows - i
-  std::vector<float> half((size_t)qr * cols);
-  for (int qi = 0; qi < qr; ++qi)
-    for (int j = 0; j < cols; ++j) half[(size_t)qi * cols + j] = quad[(size_t)qi * qc + (std::abs(2 * j - cols) >> 1)];
+  build_vignetting_quadrant(orows, ocols, q.vig_scale, q.vig_a2, q.vig_a4, quad, qr, qc);
+  std::vector<float> full((size_t)rows * cols);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      int oy = y, ox = x;  // flip.cpp:37-58 as destination coordinates (inverse of frame_math.cuh flip_source)
+      if (angle == 90) { oy = x; ox = rows - 1 - y; }
+      else if (angle == 180) { oy = rows - 1 - y; ox = cols - 1 - x; }
+      else if (angle == 270) { oy = cols - 1 - x; ox = y; }
+      full[(size_t)y * cols + x] = quad[(size_t)(std::abs(2 * oy - orows) >> 1) * qc + (std::abs(2 * ox - ocols) >> 1)];
+    }
   RIP_CUDA(p, cudaDeviceSynchronize());
-  RIP_CUDA(p, p->d_vig.reserve(half.size() * sizeof(float)));
-  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, half.data(), half.size() * sizeof(float), cudaMemcpyHostToDevice));
-  p->vig_rows = rows; p->vig_cols = cols; p->vig_pitch = cols; memcpy(p->vig_par, par, sizeof par);
+  RIP_CUDA(p, p->d_vig.reserve(full.size() * sizeof(float)));
+  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, full.data(), full.size() * sizeof(float), cudaMemcpyHostToDevice));
+  p->vig_rows = rows; p->vig_cols = cols; p->vig_angle = angle; p->vig_pitch = cols; memcpy(p->vig_par, par, sizeof par);
   return RIP_OK;
 }
 
@@ -314,7 +323,7 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   const bool undistort = g.undistort && !use_override;
   int launches = 0;
   if (stages & (ST_GAMMA | ST_VIG | ST_ENH)) { int rc = ensure_tables(p); if (rc != RIP_OK) return rc; }
-  if (stages & ST_VIG) { int rc = ensure_vignetting(p, g.frows, g.fcols); if (rc != RIP_OK) return rc; }
+  if (stages & ST_VIG) { int rc = ensure_vignetting(p, g.rows, g.cols, g.angle); if (rc != RIP_OK) return rc; }
   if (undistort) { int rc = ensure_map(p); if (rc != RIP_OK) return rc; }
 
   FrameParams fp{};

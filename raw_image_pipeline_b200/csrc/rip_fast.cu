@@ -180,6 +180,18 @@ __device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRo
   Bw = row_has_r ? other_colour : row_colour;
 }
 
+// the same quad straight from global memory (edge tiles only, see k_fused_fast)
+__device__ __noinline__ void quad_bgr_words_global(const FrameParams& P, int frame, int y, int x, uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const uint8_t* fin = P.in + (long long)frame * P.in_frame_stride;
+  Bw = Gw = Rw = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int b, g, r;
+    demosaic_at(fin, P.rows, P.cols, (size_t)P.in_pitch, y, x + k, P.cfa, b, g, r);
+    Bw |= (uint32_t)b << (8 * k); Gw |= (uint32_t)g << (8 * k); Rw |= (uint32_t)r << (8 * k);
+  }
+}
+
 // =============================================================================================
 // fused kernel, fast path
 // =============================================================================================
@@ -244,33 +256,25 @@ __global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ Fr
     uint8_t* s_out = sm.out;
     const int x = c.x0 + 4 * lane;
     const bool x_in = x >= 0 && x < P.cols;
+    // The frame's last row opens a tile (rows % TH == 1), or its first row closes one (same, rotated by 180): the border
+    // rule needs a Bayer row two above / below the tile, outside the staged halo.  One single-row tile row per frame.
+    const bool edge_tile = c.y0 == P.rows - 1 || c.y0 == 1 - TH;
 #pragma unroll 1
     for (int rr = 0; rr < TH / 8 && x_in; ++rr) {
       const int r_in_tile = warp + 8 * rr;
       const int y = c.y0 + r_in_tile;
       if ((unsigned)y >= (unsigned)P.rows) continue;
       uint32_t Bw, Gw, Rw;
-      const int sr = min(max(y, 1), P.rows - 2) - c.y0;  // staged row above the (clamped) centre row
-      if (sr >= 0 && sr + 2 <= TH + 1) {
+      if (!edge_tile) {
         quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
       } else {
-        // The frame's last row opens a tile (rows % TH == 1), or its first row closes one (same, rotated by 180): the
-        // border rule needs a Bayer row two above / below the tile, outside the staged halo.  One row per frame.
-        const uint8_t* fin = P.in + (long long)c.frame * P.in_frame_stride;
-        Bw = Gw = Rw = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int b, g, r;
-          demosaic_at(fin, P.rows, P.cols, (size_t)P.in_pitch, y, x + k, P.cfa, b, g, r);
-          Bw |= (uint32_t)b << (8 * k); Gw |= (uint32_t)g << (8 * k); Rw |= (uint32_t)r << (8 * k);
-        }
+        quad_bgr_words_global(P, c.frame, y, x, Bw, Gw, Rw);
       }
-      const int oy = rev ? P.rows - 1 - y : y;
       const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
       float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-      if (STAGES & ST_VIG) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch + oxb));
-        if (rev) { m[0] = v.w; m[1] = v.z; m[2] = v.y; m[3] = v.x; } else { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+      if (STAGES & ST_VIG) {  // mask table is stored in input-frame coordinates
+        const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + (size_t)y * P.vig_pitch + x));
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
       }
       uint32_t px[4];
       if ((STAGES & ST_ENH) && oxb >= tail_start) {  // whole quad lies in cv2's scalar row tail (rare: width % 32 != 0)

@@ -148,41 +148,28 @@ __device__ __forceinline__ void copy_row(uint8_t* dst, const uint8_t* src, int n
   }
 }
 
-// =============================================================================================
-// fused kernel
-// =============================================================================================
 // vignetting-mask values and cv2 row-tail flags of the four pixels (y, x..x+3) a thread owns
 template <uint32_t STAGES>
 __device__ __forceinline__ void quad_position_inputs(const FrameParams& P, int y, int x, float m[4], bool tail[4]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) { m[k] = 1.0f; tail[k] = false; }
-  if (!(STAGES & (ST_VIG | ST_ENH))) return;
-  const int tail_start = P.ocols & ~31;  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
-  if (P.angle == 0 || P.angle == 180) {
-    const bool rev = P.angle == 180;
-    const int oy = rev ? P.rows - 1 - y : y;
-    const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
-    if (STAGES & ST_VIG) {
-      const float* mrow = P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch;
-      if (x + 3 < P.cols && ((P.vig_pitch | oxb) & 3) == 0) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(mrow + oxb));
-        if (rev) { m[0] = v.w; m[1] = v.z; m[2] = v.y; m[3] = v.x; } else { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
-      } else {
+  if (STAGES & ST_VIG) {  // the mask table is stored in input-frame coordinates
+    const float* mrow = P.vig + (size_t)y * P.vig_pitch + x;
+    if (x + 3 < P.cols && ((P.vig_pitch | x) & 3) == 0) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(mrow));
+      m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (x + k < P.cols) m[k] = __ldg(mrow + (rev ? P.cols - 1 - x - k : x + k));
-      }
+      for (int k = 0; k < 4; ++k)
+        if (x + k < P.cols) m[k] = __ldg(mrow + k);
     }
-    if (STAGES & ST_ENH) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) tail[k] = (rev ? P.cols - 1 - x - k : x + k) >= tail_start;
-    }
-  } else {
+  }
+  if (STAGES & ST_ENH) {
+    const int tail_start = P.ocols & ~31;  // cv2's scalar row tail in HSV2BGR (pixel_math.cuh)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int oy, ox;
       flip_dest(P.angle, P.rows, P.cols, y, min(x + k, P.cols - 1), oy, ox);
-      if (STAGES & ST_VIG) m[k] = __ldg(P.vig + (size_t)(abs(2 * oy - P.orows) >> 1) * P.vig_pitch + ox);
       tail[k] = ox >= tail_start;
     }
   }
