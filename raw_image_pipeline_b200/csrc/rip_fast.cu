@@ -181,15 +181,16 @@ __device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRo
 }
 
 // the same quad straight from global memory (edge tiles only, see k_fused_fast)
-__device__ __noinline__ void quad_bgr_words_global(const FrameParams& P, int frame, int y, int x, uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+__device__ __noinline__ uint3 quad_bgr_words_global(const FrameParams& P, int frame, int y, int x) {
   const uint8_t* fin = P.in + (long long)frame * P.in_frame_stride;
-  Bw = Gw = Rw = 0;
+  uint32_t Bw = 0, Gw = 0, Rw = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     int b, g, r;
     demosaic_at(fin, P.rows, P.cols, (size_t)P.in_pitch, y, x + k, P.cfa, b, g, r);
     Bw |= (uint32_t)b << (8 * k); Gw |= (uint32_t)g << (8 * k); Rw |= (uint32_t)r << (8 * k);
   }
+  return make_uint3(Bw, Gw, Rw);
 }
 
 // =============================================================================================
@@ -198,8 +199,8 @@ __device__ __noinline__ void quad_bgr_words_global(const FrameParams& P, int fra
 template <uint32_t STAGES, bool BGRX>
 __global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ FrameParams P, const __grid_constant__ CUtensorMap in_map,
                                                    const __grid_constant__ CUtensorMap out_map) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  FastSmem<BGRX>& sm = *reinterpret_cast<FastSmem<BGRX>*>(smem_raw);
+  // static shared memory (< 48 KB): table addresses are link-time constants, so lookups are `LDS [index + constant]`
+  __shared__ FastSmem<BGRX> sm;
   constexpr int OUT_PITCH = OutFmt<BGRX>::PITCH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ Fr
       if (!edge_tile) {
         quad_bgr_words(s_in, P.rows, P.cols, P.cfa, c.y0, y, x, lane, Bw, Gw, Rw);
       } else {
-        quad_bgr_words_global(P, c.frame, y, x, Bw, Gw, Rw);
+        const uint3 w = quad_bgr_words_global(P, c.frame, y, x);
+        Bw = w.x; Gw = w.y; Rw = w.z;
       }
       const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
       float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
@@ -466,22 +468,20 @@ template <uint32_t S, bool BGRX>
 cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorMap& im, const CUtensorMap& om, int sm_count,
                           cudaStream_t stream) {
   if (stages == S) {
-    static int occ_of_device[64] = {0};  // per instantiation and device: the shared-memory opt-in is a per-device attribute
-    constexpr size_t smem = sizeof(FastSmem<BGRX>);
+    static int occ_of_device[64] = {0};  // per instantiation and device
+    static_assert(sizeof(FastSmem<BGRX>) <= 48 * 1024, "k_fused_fast keeps its shared memory static");
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     int& occ = occ_of_device[dev & 63];
     if (occ == 0) {
-      e = cudaFuncSetAttribute(k_fused_fast<S, BGRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S, BGRX>, NT, smem);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_fast<S, BGRX>, NT, 0);
       if (e != cudaSuccess) return e;
       if (occ < 1) occ = 1;
     }
     const long long tiles = total_tiles(p, TH), cap = (long long)sm_count * occ;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    k_fused_fast<S, BGRX><<<grid, NT, smem, stream>>>(p, im, om);
+    k_fused_fast<S, BGRX><<<grid, NT, 0, stream>>>(p, im, om);
     return cudaGetLastError();
   }
   if constexpr (S < ST_ALL) return dispatch_fast<S + 1, BGRX>(stages, p, im, om, sm_count, stream);
