@@ -198,11 +198,36 @@ RIP_HD bool remap_pack_entry(float mx, float my, int x, int y, int rows, int col
   packed = (uint32_t)(uint16_t)dx | ((uint32_t)(uint16_t)dy << 16);
   return true;
 }
-RIP_HD uint32_t remap_pixel_bgrx_packed(const uint32_t* src, int rows, int cols, int pitch_px, uint32_t packed, int x, int y) {
+RIP_HD void remap_unpack_entry(uint32_t packed, int x, int y, int& sx, int& sy) {
   const int dx = (int)(int16_t)(packed & 0xffffu), dy = (int)(int16_t)(packed >> 16);
   // REMAP_FAR -> a coordinate no image contains: every tap fails the bounds tests and the result is 0
-  const int sx = dx == REMAP_FAR ? INT32_MIN : 32 * x + dx;
-  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, sx, 32 * y + dy);
+  sx = dx == REMAP_FAR ? INT32_MIN : 32 * x + dx;
+  sy = 32 * y + dy;
+}
+RIP_HD uint32_t remap_pixel_bgrx_packed(const uint32_t* src, int rows, int cols, int pitch_px, uint32_t packed, int x, int y) {
+  int sx, sy;
+  remap_unpack_entry(packed, x, y, sx, sy);
+  return remap_pixel_bgrx_fix(src, rows, cols, pitch_px, sx, sy);
+}
+// integer parts of a packed entry's displacement (floor(d / 32)); the low 5 bits of each half are the 1/32 fractions
+RIP_HD int remap_packed_dxi(uint32_t packed) { return (int)(packed << 16) >> 21; }
+RIP_HD int remap_packed_dyi(uint32_t packed) { return (int)packed >> 21; }
+// The blend of remap_pixel_bgrx_fix for taps that are already in registers (tile kernel, rip_fast.cu).  The vertical
+// weights carry a factor 64, which puts (V + 512) >> 10 into byte 2 of each sum (V * 64 + 2^15 < 2^24), so the three
+// channels are packed by two byte permutes.  Returns b | g << 8 | r << 16.
+RIP_HD uint32_t remap_blend_w(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t ax, uint32_t ay6) {
+  const uint32_t by6 = 2048u - ay6;
+  const uint32_t wA = ax * 255u + 32u;  // bytes (32 - ax, ax, 0, 0)
+  const uint32_t wB = wA << 16;         // bytes (0, 0, 32 - ax, ax)
+  const uint32_t bg0 = prmt(t00, t01, 0x5140u), bg1 = prmt(t10, t11, 0x5140u);  // B00 B01 G00 G01
+  const uint32_t r0 = prmt(t00, t01, 0x3362u), r1 = prmt(t10, t11, 0x3362u);    // R00 R01 0 0 (byte 3 of a pixel is 0)
+  const uint32_t vb = by6 * dot4_u8(bg0, wA) + ay6 * dot4_u8(bg1, wA) + 0x8000u;
+  const uint32_t vg = by6 * dot4_u8(bg0, wB) + ay6 * dot4_u8(bg1, wB) + 0x8000u;
+  const uint32_t vr = by6 * dot4_u8(r0, wA) + ay6 * dot4_u8(r1, wA) + 0x8000u;
+  return prmt(prmt(vb, vg, 0x3362u), vr, 0x7610u);  // bytes: vb.2, vg.2, vr.2, vr.3 (= 0)
+}
+RIP_HD uint32_t remap_blend(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, int sx, int sy) {
+  return remap_blend_w(t00, t01, t10, t11, (uint32_t)(sx & 31), ((uint32_t)sy & 31u) << 6);
 }
 
 // ---- PCA white balance: white_balance.cpp:73-136 ----------------------------

@@ -39,7 +39,18 @@ struct RemapParams {
   int n_frames;
   const float2* map;   // orows x ocols (x, y)
   const uint32_t* pmap;  // optional packed fixed-point map (frame_math.cuh remap_pack_entry), used by launch_remap_bgrx when set
+  const int4* tiles;     // optional tile table of the packed map (remap_tile_table), used by launch_remap_tile
+  const uint32_t* tmap;  // ... and the packed map padded to whole tiles, `tmap_pitch` entries per row
+  int tmap_pitch;
 };
+
+// Tile geometry of launch_remap_tile and its host-side table: per REMAP_TILE_W x REMAP_TILE_H output tile
+// {bx0, by0, flags, 0} = origin of the source box (bx0 % 4 == 0) and REMAP_TILE_FAST when every tap of every pixel of
+// the tile lies inside the REMAP_BOX_W x REMAP_BOX_H box at that origin and no entry is "far".
+constexpr int REMAP_TILE_W = 128, REMAP_TILE_H = 24, REMAP_BOX_W = 176, REMAP_BOX_H = 48;
+constexpr int REMAP_TILE_FAST = 1;
+// `padded`: the packed map padded to whole tiles (ceil(ocols / W) * W entries per row, ceil(orows / H) * H rows)
+void remap_tile_table(const uint32_t* packed, int orows, int ocols, int* table /* 4 ints per tile, row-major tiles */, uint32_t* padded);
 
 // All launchers enqueue on `stream`, return the CUDA error of the launch, and add the number of
 // kernels launched to *launches.
@@ -61,5 +72,8 @@ cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, i
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
 // same remap from a 4-byte-per-pixel B,G,R,0 source (p.pitch = cols * 4) to BGR8
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches);
+// tile path of the same (rip_fast.cu): TMA-staged source boxes, needs the packed map and ocols % 4 == 0
+bool remap_tile_ok(const RemapParams& p);
+cudaError_t launch_remap_tile(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches);
 
 }  // namespace rip

@@ -75,6 +75,7 @@ struct rip_pipeline {
   bool profile = false;
   bool force_generic = false;  // "debug/force_generic_kernels": tests run both kernel families
   bool force_float_map = false;  // "debug/force_float_map": undistortion reads the fp32 map even where the packed one exists
+  bool force_gather_remap = false;  // "debug/force_gather_remap": undistortion gathers from global memory even where the tile kernel applies
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
     if (!profile) return cudaSuccess;
@@ -94,6 +95,7 @@ struct rip_pipeline {
   DevBuf d_tables; bool tables_valid = false; ChainTableParams tables_key;
   DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_angle = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
   DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
+  DevBuf d_tiles, d_tmap; int tmap_pitch = 0;  // tile table and tile-padded copy of the packed map (kernels.hpp remap_tile_table)
   DevBuf d_pmap; bool pmap_ok = false; int pmap_src_rows = -1, pmap_src_cols = -1; uint64_t pmap_epoch = 0;  // packed fixed-point map
   std::vector<float> h_map;  // host copy (debug / tests)
   CccState ccc;
@@ -301,6 +303,16 @@ int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
     RIP_CUDA(p, cudaDeviceSynchronize());
     RIP_CUDA(p, p->d_pmap.reserve(packed.size() * sizeof(uint32_t)));
     RIP_CUDA(p, cudaMemcpy(p->d_pmap.ptr, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    // source footprint of every output tile and the tile-padded copy of the map (launch_remap_tile)
+    const int tiles_x = (w + REMAP_TILE_W - 1) / REMAP_TILE_W, tiles_y = (h + REMAP_TILE_H - 1) / REMAP_TILE_H;
+    std::vector<int> table((size_t)4 * tiles_x * tiles_y);
+    std::vector<uint32_t> padded((size_t)tiles_x * REMAP_TILE_W * tiles_y * REMAP_TILE_H);
+    remap_tile_table(packed.data(), h, w, table.data(), padded.data());
+    RIP_CUDA(p, p->d_tiles.reserve(table.size() * sizeof(int)));
+    RIP_CUDA(p, cudaMemcpy(p->d_tiles.ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    RIP_CUDA(p, p->d_tmap.reserve(padded.size() * sizeof(uint32_t)));
+    RIP_CUDA(p, cudaMemcpy(p->d_tmap.ptr, padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    p->tmap_pitch = tiles_x * REMAP_TILE_W;
   }
   p->pmap_epoch = p->hs.und_epoch; p->pmap_src_rows = src_rows; p->pmap_src_cols = src_cols;
   return RIP_OK;
@@ -387,10 +399,11 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     if (bgrx && !p->force_float_map) {
       int rc = ensure_packed_map(p, g.frows, g.fcols);
       if (rc != RIP_OK) return rc;
-      if (p->pmap_ok) rp.pmap = p->d_pmap.as<uint32_t>();
+      if (p->pmap_ok) { rp.pmap = p->d_pmap.as<uint32_t>(); rp.tiles = p->d_tiles.as<int4>(); rp.tmap = p->d_tmap.as<uint32_t>(); rp.tmap_pitch = p->tmap_pitch; }
     }
     RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_REMAP, stream));
-    if (bgrx) RIP_CUDA(p, launch_remap_bgrx(rp, p->sm_count, stream, &launches));
+    if (bgrx && !p->force_gather_remap && remap_tile_ok(rp)) RIP_CUDA(p, launch_remap_tile(rp, p->sm_count, stream, &launches));
+    else if (bgrx) RIP_CUDA(p, launch_remap_bgrx(rp, p->sm_count, stream, &launches));
     else RIP_CUDA(p, launch_remap(och, rp, stream, &launches));
     RIP_CUDA(p, p->span_end(stream));
   }
@@ -495,6 +508,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "profile/kernel_events")) p->profile = v;
   else if (key_is(key, "debug/force_generic_kernels")) p->force_generic = v;
   else if (key_is(key, "debug/force_float_map")) p->force_float_map = v;
+  else if (key_is(key, "debug/force_gather_remap")) p->force_gather_remap = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;

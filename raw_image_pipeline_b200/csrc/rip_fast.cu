@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "frame_math.cuh"
 #include "kernels.hpp"
@@ -424,6 +425,150 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
   if (cur_frame >= 0) flush(cur_frame);
 }
 
+// =============================================================================================
+// undistortion, tile path (undistortion.cpp:214-245 -> cv::remap INTER_LINEAR, BORDER_CONSTANT 0)
+// =============================================================================================
+// An output tile of RT_W x RT_H pixels gathers from a compact region of the 4-byte intermediate.  The host knows that
+// region for every tile (remap_tile_table, built once per map): a producer warp has the TMA unit copy a fixed
+// BOX_W x BOX_H-pixel box at the footprint's origin into shared memory, two tiles ahead of the consumers; rows and
+// columns of the box outside the image arrive as zeros, which is cv::remap's constant border.  Eight consumer warps
+// gather the four taps of each pixel from shared memory (lane <-> adjacent pixels: conflict-free), blend, and exchange
+// the packed results through a per-warp row so that every lane stores 12 contiguous bytes.  Tiles whose footprint fits
+// the box and that hold no "far" entry (the common case) run without any per-pixel test; the others test every pixel
+// and take the global-memory gather of the generic kernel where the box does not reach.
+constexpr int RT_W = REMAP_TILE_W, RT_H = REMAP_TILE_H, BOX_W = REMAP_BOX_W, BOX_H = REMAP_BOX_H;
+constexpr int RT_STAGES = 2;
+constexpr int RT_CONSUMERS = 8, RT_THREADS = (RT_CONSUMERS + 1) * 32;
+constexpr int BOX_BYTES = BOX_W * BOX_H * 4;
+constexpr int RT_ROWS_WARP = RT_H / RT_CONSUMERS;  // consecutive tile rows owned by a warp, one per iteration
+static_assert(RT_W == 128 && RT_H % RT_CONSUMERS == 0, "a warp covers one 128-pixel tile row per iteration");
+
+struct RemapTileSmem {
+  alignas(128) uint32_t box[RT_STAGES][BOX_W * BOX_H];
+  alignas(16) uint32_t px[RT_CONSUMERS][RT_W];
+  int origin[RT_STAGES][4];  // bx0, by0, flags
+  alignas(8) unsigned long long full[RT_STAGES], empty[RT_STAGES];
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// one pixel of a tile without the FAST flag: shared-memory taps when they are inside the box, else the global gather
+__device__ __noinline__ uint32_t remap_tile_pixel_slow(const RemapParams& P, const uint32_t* box, int bx0, int by0, const uint32_t* src,
+                                                       int sx, int sy) {
+  const int rx = (sx >> 5) - bx0, ry = (sy >> 5) - by0;
+  if ((unsigned)rx < (unsigned)(BOX_W - 1) && (unsigned)ry < (unsigned)(BOX_H - 1)) {
+    const uint32_t* q = box + ry * BOX_W + rx;
+    return remap_blend(q[0], q[1], q[BOX_W], q[BOX_W + 1], sx, sy);
+  }
+  return remap_pixel_bgrx_fix(src, P.rows, P.cols, P.pitch >> 2, sx, sy);
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_constant__ RemapParams P, const __grid_constant__ CUtensorMap src_map) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  RemapTileSmem& sm = *reinterpret_cast<RemapTileSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (P.ocols + RT_W - 1) / RT_W, tiles_y = (P.orows + RT_H - 1) / RT_H;
+  const long long tiles_per_frame = (long long)tiles_x * tiles_y;
+  const long long total = tiles_per_frame * P.n_frames;
+  if (tid == 0) {
+    for (int i = 0; i < RT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], RT_CONSUMERS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  long long t = total * blockIdx.x / gridDim.x;
+  const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  TileIter ti;
+  ti.init(t, tiles_x, tiles_per_frame);
+
+  if (warp == RT_CONSUMERS) {
+    // ---- producer warp ----
+    int buf = 0; uint32_t round = 0;
+    for (; t < t_end; ++t, ti.advance(tiles_x, tiles_y)) {
+      const int4 info = __ldg(P.tiles + (ti.ty * tiles_x + ti.tx));
+      // L2 prefetch of the tile's map rows (the consumers read them when they reach this tile)
+      const int x0 = ti.tx * RT_W, y0 = ti.ty * RT_H;
+      if (lane < RT_H)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.tmap + (size_t)(y0 + lane) * P.tmap_pitch + x0), "r"(RT_W * 4) : "memory");
+      if (round > 0) mbar_wait(&sm.empty[buf], (round - 1) & 1u);
+      if (lane == 0) {
+        sm.origin[buf][0] = info.x; sm.origin[buf][1] = info.y; sm.origin[buf][2] = info.z;
+        mbar_expect_tx(&sm.full[buf], BOX_BYTES);
+        tma_load_3d(sm.box[buf], &src_map, &sm.full[buf], info.x, info.y, ti.frame);
+      }
+      __syncwarp();
+      if (++buf == RT_STAGES) { buf = 0; ++round; }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  // lane l, slot k: column x0 + l + 32 k of the iteration's row.  The four map entries of an iteration are loaded one
+  // iteration ahead (across tile boundaries too) from the tile-padded copy of the map (remap_tile_table): entries beyond
+  // the image edge point at the edge pixel's source position, so they need no special case (and are never stored).
+  auto map_load = [&](const TileIter& q, int i, uint32_t mm[4]) {
+    const uint32_t* row = P.tmap + (size_t)(q.ty * RT_H + warp * RT_ROWS_WARP + i) * P.tmap_pitch + (q.tx * RT_W + lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mm[k] = __ldg(row + 32 * k);
+  };
+  int buf = 0; uint32_t round = 0;
+  uint32_t mc[4] = {0u, 0u, 0u, 0u};
+  if (t < t_end) map_load(ti, 0, mc);
+  TileIter tn = ti;
+  for (; t < t_end; ++t, ti.advance(tiles_x, tiles_y)) {
+    const int x0 = ti.tx * RT_W, yw = ti.ty * RT_H + warp * RT_ROWS_WARP;
+    tn.advance(tiles_x, tiles_y);
+    mbar_wait(&sm.full[buf], round & 1u);
+    const int bx0 = sm.origin[buf][0], by0 = sm.origin[buf][1];
+    const bool fast = (sm.origin[buf][2] & REMAP_TILE_FAST) != 0;
+    const uint32_t* box = sm.box[buf];
+    uint8_t* drow = P.dst + (long long)ti.frame * P.dst_frame_stride + (size_t)yw * P.dpitch + (size_t)(x0 + 4 * lane) * 3;
+#pragma unroll
+    for (int i = 0; i < RT_ROWS_WARP; ++i, drow += P.dpitch) {
+      uint32_t mn[4] = {0u, 0u, 0u, 0u};
+      if (i + 1 < RT_ROWS_WARP) map_load(ti, i + 1, mn);
+      else if (t + 1 < t_end) map_load(tn, 0, mn);
+      const int ya = yw + i;
+      uint32_t p[4];
+      if (fast) {
+        // every tap of every pixel of this tile lies inside the box, and no entry is "far"
+        const uint32_t* rowbase = box + ((ya - by0) * BOX_W + (x0 + lane - bx0));
+        uint32_t tp[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t* q = rowbase + 32 * k + (remap_packed_dyi(mc[k]) * BOX_W + remap_packed_dxi(mc[k]));
+          tp[k][0] = q[0]; tp[k][1] = q[1]; tp[k][2] = q[BOX_W]; tp[k][3] = q[BOX_W + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = remap_blend_w(tp[k][0], tp[k][1], tp[k][2], tp[k][3], mc[k] & 31u, (mc[k] >> 10) & 0x7c0u);
+      } else {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)ti.frame * P.src_frame_stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int sx, sy;
+          remap_unpack_entry(mc[k], x0 + lane + 32 * k, ya, sx, sy);
+          p[k] = remap_tile_pixel_slow(P, box, bx0, by0, src, sx, sy);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm.px[warp][lane + 32 * k] = p[k];
+      __syncwarp();
+      const uint4 q = *reinterpret_cast<const uint4*>(&sm.px[warp][4 * lane]);  // 4 consecutive pixels
+      __syncwarp();
+      if (x0 + 4 * lane < P.ocols && ya < P.orows) {  // ocols % 4 == 0 (launcher): the quad is complete
+        uint32_t* d = reinterpret_cast<uint32_t*>(drow);
+        d[0] = prmt(q.x, q.y, 0x4210); d[1] = prmt(q.y, q.z, 0x5421); d[2] = prmt(q.z, q.w, 0x6542);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mc[k] = mn[k];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[buf]);  // this warp is done reading box[buf]
+    if (++buf == RT_STAGES) { buf = 0; ++round; }
+  }
+}
+
 // ---- tensor maps ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -533,6 +678,76 @@ cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream
   const int grid = (int)(tiles < cap ? tiles : cap);
   if (launches) ++*launches;
   k_pca_stats_fast<<<grid, NT, 0, stream>>>(p, im);
+  return cudaGetLastError();
+}
+
+bool remap_tile_ok(const RemapParams& p) {
+  if (!p.tmap || !p.tiles || (p.ocols & 3) != 0 || p.ocols < 4 || p.orows < 1 || p.n_frames < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(p.src) & 15) != 0 || (p.pitch & 15) != 0 || p.pitch != p.cols * 4) return false;
+  if ((reinterpret_cast<uintptr_t>(p.dst) & 3) != 0 || (p.dpitch & 3) != 0 || (p.dst_frame_stride & 3) != 0) return false;
+  if (p.n_frames > 1 && (p.src_frame_stride % 16 != 0 || p.src_frame_stride <= 0)) return false;
+  return encode_tiled_fn() != nullptr;
+}
+
+void remap_tile_table(const uint32_t* packed, int orows, int ocols, int* table, uint32_t* padded) {
+  const int tiles_x = (ocols + RT_W - 1) / RT_W, tiles_y = (orows + RT_H - 1) / RT_H;
+  const int pw = tiles_x * RT_W, ph = tiles_y * RT_H;
+  const uint32_t far_entry = 0x80008000u;  // REMAP_FAR in both halves
+  // the map padded to whole tiles: a padding entry at (x, y) carries the edge entry's displacement re-based to (x, y)
+  for (int y = 0; y < ph; ++y)
+    for (int x = 0; x < pw; ++x) {
+      const int xc = x < ocols ? x : ocols - 1, yc = y < orows ? y : orows - 1;
+      uint32_t e = packed[(size_t)yc * ocols + xc];
+      if ((x != xc || y != yc) && (e & 0xffffu) != 0x8000u) {
+        const int dx = (int)(int16_t)(e & 0xffffu) - 32 * (x - xc), dy = (int)(int16_t)(e >> 16) - 32 * (y - yc);
+        e = (dx > REMAP_FAR && dy > REMAP_FAR) ? ((uint32_t)(uint16_t)dx | ((uint32_t)(uint16_t)dy << 16)) : far_entry;
+      }
+      padded[(size_t)y * pw + x] = e;
+    }
+  for (int ty = 0; ty < tiles_y; ++ty)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      int ix_lo = INT32_MAX, ix_hi = INT32_MIN, iy_lo = INT32_MAX, iy_hi = INT32_MIN;
+      bool far = false;
+      for (int y = ty * RT_H; y < ty * RT_H + RT_H; ++y)
+        for (int x = tx * RT_W; x < tx * RT_W + RT_W; ++x) {
+          const uint32_t e = padded[(size_t)y * pw + x];
+          if ((e & 0xffffu) == 0x8000u) { far = true; continue; }
+          const int ix = x + remap_packed_dxi(e), iy = y + remap_packed_dyi(e);
+          ix_lo = ix < ix_lo ? ix : ix_lo; ix_hi = ix > ix_hi ? ix : ix_hi;
+          iy_lo = iy < iy_lo ? iy : iy_lo; iy_hi = iy > iy_hi ? iy : iy_hi;
+        }
+      int* t = table + 4 * ((size_t)ty * tiles_x + tx);
+      if (ix_lo == INT32_MAX) { t[0] = 0; t[1] = 0; t[2] = 0; t[3] = 0; continue; }  // nothing maps into the source
+      const int bx0 = ix_lo & ~3;  // floor to a multiple of 4 pixels: 16-byte aligned TMA coordinate
+      const bool fits = ix_hi + 1 - bx0 <= BOX_W - 1 && iy_hi + 1 - iy_lo <= BOX_H - 1;
+      t[0] = bx0; t[1] = iy_lo; t[2] = (fits && !far) ? REMAP_TILE_FAST : 0; t[3] = 0;
+    }
+}
+
+cudaError_t launch_remap_tile(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches) {
+  CUtensorMap sm;
+  const cuuint64_t fstride = p.n_frames > 1 ? (cuuint64_t)p.src_frame_stride : (cuuint64_t)p.pitch * p.rows;
+  if (!make_map(&sm, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.src, (cuuint64_t)p.cols, (cuuint64_t)p.rows, (cuuint64_t)p.n_frames,
+                (cuuint64_t)p.pitch, fstride, BOX_W, BOX_H))
+    return cudaErrorInvalidValue;
+  static int occ_of_device[64] = {0};  // per device: the shared-memory opt-in is a per-device attribute
+  constexpr size_t smem = sizeof(RemapTileSmem);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int& occ = occ_of_device[dev & 63];
+  if (occ == 0) {
+    e = cudaFuncSetAttribute(k_remap_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_remap_tile, RT_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+  }
+  const long long tiles = (long long)((p.ocols + RT_W - 1) / RT_W) * ((p.orows + RT_H - 1) / RT_H) * p.n_frames;
+  const long long cap = (long long)sm_count * occ;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  if (launches) ++*launches;
+  k_remap_tile<<<grid, RT_THREADS, smem, stream>>>(p, sm);
   return cudaGetLastError();
 }
 
