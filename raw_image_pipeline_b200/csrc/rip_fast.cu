@@ -121,6 +121,24 @@ struct TileIter {
   }
 };
 
+// advance a TileIter by a fixed number of tiles (the grid size) without divisions
+struct TileStride {
+  int gx, gy, gf;
+  __device__ __forceinline__ void init(int g, int tiles_x, int tiles_y) {
+    gx = g % tiles_x;
+    const int r = g / tiles_x;
+    gy = r % tiles_y;
+    gf = r / tiles_y;
+  }
+  __device__ __forceinline__ void advance(TileIter& q, int tiles_x, int tiles_y) const {
+    q.tx += gx;
+    if (q.tx >= tiles_x) { q.tx -= tiles_x; ++q.ty; }
+    q.ty += gy;
+    if (q.ty >= tiles_y) { q.ty -= tiles_y; ++q.frame; }
+    q.frame += gf;
+  }
+};
+
 // packed B / G / R words of the four pixels (y, x .. x+3); `s_in` is the staged tile whose row 0 is y0 - 1
 __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, int cols, int cfa, int y0, int y, int x, int lane,
                                                uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
@@ -477,15 +495,19 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
     fence_mbar_init();
   }
   __syncthreads();
-  long long t = total * blockIdx.x / gridDim.x;
-  const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+  // Tiles are dealt round-robin: CTA c takes tiles c, c + G, c + 2G, ...  The CTAs then work on one band of adjacent tile
+  // rows at a time, so the rows that vertically adjacent boxes share are still in L2 when the next tile row asks for them.
+  long long t = blockIdx.x;
+  const long long t_end = total;
+  TileStride ts;
+  ts.init((int)gridDim.x, tiles_x, tiles_y);
   TileIter ti;
   ti.init(t, tiles_x, tiles_per_frame);
 
   if (warp == RT_CONSUMERS) {
     // ---- producer warp ----
     int buf = 0; uint32_t round = 0;
-    for (; t < t_end; ++t, ti.advance(tiles_x, tiles_y)) {
+    for (; t < t_end; t += gridDim.x, ts.advance(ti, tiles_x, tiles_y)) {
       const int4 info = __ldg(P.tiles + (ti.ty * tiles_x + ti.tx));
       // L2 prefetch of the tile's map rows (the consumers read them when they reach this tile)
       const int x0 = ti.tx * RT_W, y0 = ti.ty * RT_H;
@@ -516,9 +538,9 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
   uint32_t mc[4] = {0u, 0u, 0u, 0u};
   if (t < t_end) map_load(ti, 0, mc);
   TileIter tn = ti;
-  for (; t < t_end; ++t, ti.advance(tiles_x, tiles_y)) {
+  for (; t < t_end; t += gridDim.x, ts.advance(ti, tiles_x, tiles_y)) {
     const int x0 = ti.tx * RT_W, yw = ti.ty * RT_H + warp * RT_ROWS_WARP;
-    tn.advance(tiles_x, tiles_y);
+    ts.advance(tn, tiles_x, tiles_y);
     mbar_wait(&sm.full[buf], round & 1u);
     const int bx0 = sm.origin[buf][0], by0 = sm.origin[buf][1];
     const bool fast = (sm.origin[buf][2] & REMAP_TILE_FAST) != 0;
@@ -528,7 +550,7 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
     for (int i = 0; i < RT_ROWS_WARP; ++i, drow += P.dpitch) {
       uint32_t mn[4] = {0u, 0u, 0u, 0u};
       if (i + 1 < RT_ROWS_WARP) map_load(ti, i + 1, mn);
-      else if (t + 1 < t_end) map_load(tn, 0, mn);
+      else if (t + gridDim.x < t_end) map_load(tn, 0, mn);
       const int ya = yw + i;
       uint32_t p[4];
       if (fast) {
