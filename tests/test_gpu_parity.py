@@ -210,6 +210,25 @@ def test_undistortion_batch_paths_packed_and_float_map(oracle_built):
             assert_same(floatmap[i], ref, f"float map frame {i} {balance} {fov}")
 
 
+@pytest.mark.parametrize("balance,fov", [(0.0, 0.8), (1.0, 1.2), (0.0, 0.45), (0.5, 2.5)])
+def test_undistortion_tile_kernel_equals_gather_kernel(oracle_built, balance, fov):
+    """The TMA-staged tile kernel (source boxes in shared memory) and the global-memory gather give the oracle's bytes:
+    mild maps (every tile takes the test-free path), 2x magnification (footprints overflow the box: per-pixel
+    fallback), strong minification with pixels mapping outside the source ("far" entries, zero border), and a
+    width/height that leave partial tiles."""
+    rows, cols, n = 540 + 16, 720 + 48, 2
+    frames = synth.bayer_batch(n, rows, cols, "bayer_gbrg8", 4200, "N")
+    kw = dict(FULL); kw["undistort"] = (balance, fov)
+    p, o = make_pair(rows, cols, **kw)
+    tile = p.process_batch(frames, "bayer_gbrg8")
+    p._set_bool("debug/force_gather_remap", True)
+    gather = p.process_batch(frames, "bayer_gbrg8")
+    for i in range(n):
+        ref, _ = o.apply(frames[i], "bayer_gbrg8")
+        assert_same(tile[i], ref, f"tile kernel frame {i} {balance} {fov}")
+        assert_same(gather[i], ref, f"gather kernel frame {i} {balance} {fov}")
+
+
 # ---- 3-channel inputs (apply_pipeline.py usage: a bgr8 PNG) ---------------------------------------
 @pytest.mark.parametrize("enc", ["bgr8", "rgb8"])
 def test_colour_input(oracle_built, enc):
