@@ -335,8 +335,10 @@ def run_b200(args):
         return kernel_ms[i] / max(kernel_ms[4 + i], 1.0)
     px = float(n) * rows * cols
     other = {
-        "k_remap_bgrx": {"algorithmic_bytes_per_px": 14, "avg_launch_ms": per_launch(3),
-                         "achieved_gbs": 14 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None},
+        # SURVEY 8d counts 14 B/px (3 gather + 8 fp32 map + 3 write); the kernel moves 11 (4-byte intermediate, packed map)
+        "k_remap_tile": {"algorithmic_bytes_per_px": 14, "moved_bytes_per_px": 11, "avg_launch_ms": per_launch(3),
+                         "achieved_gbs": 14 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None,
+                         "moved_gbs": 11 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None},
         "k_pca_stats": {"algorithmic_bytes_per_px": 1, "avg_launch_ms": per_launch(0),
                         "achieved_gbs": px / (per_launch(0) * 1e-3) / 1e9 if per_launch(0) > 0 else None},
         "whole_step": {"algorithmic_bytes_per_px": 19, "ms": ms_total / args.steps,
@@ -345,6 +347,8 @@ def run_b200(args):
     for v in other.values():
         if v.get("achieved_gbs"):
             v["frac_of_peak"] = v["achieved_gbs"] / peak
+        if v.get("moved_gbs"):
+            v["moved_frac_of_peak"] = v["moved_gbs"] / peak
     if witness and witness.get("achieved_gbs"):
         witness["frac_of_peak"] = witness["achieved_gbs"] / peak
     traffic = None

@@ -99,7 +99,8 @@ RIP_API int rip_reset_white_balance_temporal_consistency(rip_pipeline* p);  /* r
  *           rip_apply), stats/kernel_ms[8] (per-kernel CUDA-event totals and counts since the last query)
  * Development switches (bool): profile/kernel_events (CUDA events around every kernel launch),
  *   debug/force_generic_kernels (skip the TMA fast path), debug/force_float_map (undistortion reads the fp32 map
- *   instead of the packed fixed-point one).  Neither changes a single output byte.                            */
+ *   instead of the packed fixed-point one), debug/force_gather_remap (undistortion gathers from global memory instead
+ *   of the TMA-staged tile kernel).  None of them changes a single output byte.                               */
 RIP_API int rip_set_bool(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_int(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_double(rip_pipeline* p, const char* key, double value);

@@ -7,7 +7,9 @@
 //   * the demosaic stencil runs on packed bytes (4 px per 32-bit word, frame_math.cuh demosaic_quad_swar);
 //   * the BGR8 tile is assembled in shared memory and leaves through one TMA store per tile
 //     (cp.async.bulk.tensor ... bulk_group), clipped to the frame by the hardware;
-//   * persistent grid: resident CTAs walk the tile list of the whole batch frame-major.
+//   * persistent grid: resident CTAs walk the tile list of the whole batch frame-major;
+//   * undistortion (k_remap_tile): a producer warp TMA-copies each output tile's source box of the 4-byte intermediate
+//     into shared memory, eight consumer warps gather and blend from there (see the kernel's header comment).
 //
 // Everything else (ragged widths, unaligned buffers, 90/270 rotations, 3-channel inputs) takes the
 // generic kernels in rip_kernels.cu; both produce identical bytes.
