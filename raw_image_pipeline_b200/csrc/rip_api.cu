@@ -287,32 +287,41 @@ int ensure_map(rip_pipeline* p) {
 
 // Packed fixed-point version of the map (4 B/px instead of 8) for a source image of rows x cols; falls back to the
 // float map when a displacement does not fit 16 bits.
-int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
-  if (p->pmap_epoch == p->hs.und_epoch && p->pmap_src_rows == src_rows && p->pmap_src_cols == src_cols) return RIP_OK;
+// Host side of the packed map: the entries, and for the tile kernel the footprint table and the tile-padded copy.
+// Returns false when a displacement does not fit 16 bits (the float map stays in use).
+bool build_host_packed_map(rip_pipeline* p, int src_rows, int src_cols, std::vector<uint32_t>& packed, std::vector<int>& table,
+                           std::vector<uint32_t>& padded, int& tmap_pitch) {
   build_host_map(p);
   const int w = p->map_w, h = p->map_h;
-  std::vector<uint32_t> packed((size_t)w * h);
-  bool ok = true;
-  for (int y = 0; y < h && ok; ++y)
+  packed.resize((size_t)w * h);
+  for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) {
       const float* m = &p->h_map[((size_t)y * w + x) * 2];
-      if (!remap_pack_entry(m[0], m[1], x, y, src_rows, src_cols, packed[(size_t)y * w + x])) { ok = false; break; }
+      if (!remap_pack_entry(m[0], m[1], x, y, src_rows, src_cols, packed[(size_t)y * w + x])) return false;
     }
-  p->pmap_ok = ok;
-  if (ok) {
+  const int tiles_x = (w + REMAP_TILE_W - 1) / REMAP_TILE_W, tiles_y = (h + REMAP_TILE_H - 1) / REMAP_TILE_H;
+  table.resize((size_t)4 * tiles_x * tiles_y);
+  padded.resize((size_t)tiles_x * REMAP_TILE_W * tiles_y * REMAP_TILE_H);
+  remap_tile_table(packed.data(), h, w, table.data(), padded.data());
+  tmap_pitch = tiles_x * REMAP_TILE_W;
+  return true;
+}
+
+int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
+  if (p->pmap_epoch == p->hs.und_epoch && p->pmap_src_rows == src_rows && p->pmap_src_cols == src_cols) return RIP_OK;
+  std::vector<uint32_t> packed, padded;
+  std::vector<int> table;
+  int pitch = 0;
+  p->pmap_ok = build_host_packed_map(p, src_rows, src_cols, packed, table, padded, pitch);
+  if (p->pmap_ok) {
     RIP_CUDA(p, cudaDeviceSynchronize());
     RIP_CUDA(p, p->d_pmap.reserve(packed.size() * sizeof(uint32_t)));
     RIP_CUDA(p, cudaMemcpy(p->d_pmap.ptr, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    // source footprint of every output tile and the tile-padded copy of the map (launch_remap_tile)
-    const int tiles_x = (w + REMAP_TILE_W - 1) / REMAP_TILE_W, tiles_y = (h + REMAP_TILE_H - 1) / REMAP_TILE_H;
-    std::vector<int> table((size_t)4 * tiles_x * tiles_y);
-    std::vector<uint32_t> padded((size_t)tiles_x * REMAP_TILE_W * tiles_y * REMAP_TILE_H);
-    remap_tile_table(packed.data(), h, w, table.data(), padded.data());
     RIP_CUDA(p, p->d_tiles.reserve(table.size() * sizeof(int)));
     RIP_CUDA(p, cudaMemcpy(p->d_tiles.ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
     RIP_CUDA(p, p->d_tmap.reserve(padded.size() * sizeof(uint32_t)));
     RIP_CUDA(p, cudaMemcpy(p->d_tmap.ptr, padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    p->tmap_pitch = tiles_x * REMAP_TILE_W;
+    p->tmap_pitch = pitch;
   }
   p->pmap_epoch = p->hs.und_epoch; p->pmap_src_rows = src_rows; p->pmap_src_cols = src_cols;
   return RIP_OK;
@@ -694,6 +703,19 @@ int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void*
     build_host_map(p);
     data.resize(p->h_map.size() * 4);
     memcpy(data.data(), p->h_map.data(), data.size());
+  } else if (key_is(name, "undistortion_packed_map") || key_is(name, "undistortion_tile_table") || key_is(name, "undistortion_tile_map")) {
+    // host-side products for a rows x cols source image: packed entries (u32, dist_h x dist_w), the tile kernel's
+    // footprint table (4 x i32 per tile) and its tile-padded copy of the packed map
+    std::vector<uint32_t> packed, padded;
+    std::vector<int> table;
+    int pitch = 0;
+    if (!build_host_packed_map(p, rows, cols, packed, table, padded, pitch))
+      return p->fail(RIP_ERR_UNSUPPORTED, "the undistortion map has displacements that do not fit the packed form");
+    const void* src = key_is(name, "undistortion_packed_map") ? (const void*)packed.data()
+                      : key_is(name, "undistortion_tile_table") ? (const void*)table.data() : (const void*)padded.data();
+    data.resize(key_is(name, "undistortion_packed_map") ? packed.size() * 4
+                : key_is(name, "undistortion_tile_table") ? table.size() * 4 : padded.size() * 4);
+    memcpy(data.data(), src, data.size());
   } else if (key_is(name, "ccc_response")) {  // last frame of the last call: 256 x 256 fp64, == cv2 response / 65536 - bias
     if (!p->ccc.d_last_response) return p->fail(RIP_ERR_INVALID_ARGUMENT, "no CCC frame processed yet");
     std::vector<double> cplx(2 * 65536);

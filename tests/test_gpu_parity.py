@@ -213,9 +213,9 @@ def test_undistortion_batch_paths_packed_and_float_map(oracle_built):
 @pytest.mark.parametrize("balance,fov", [(0.0, 0.8), (1.0, 1.2), (0.0, 0.45), (0.5, 2.5)])
 def test_undistortion_tile_kernel_equals_gather_kernel(oracle_built, balance, fov):
     """The TMA-staged tile kernel (source boxes in shared memory) and the global-memory gather give the oracle's bytes:
-    mild maps (every tile takes the test-free path), 2x magnification (footprints overflow the box: per-pixel
-    fallback), strong minification with pixels mapping outside the source ("far" entries, zero border), and a
-    width/height that leave partial tiles."""
+    mild and zoomed-in maps (every tile takes the test-free path), zoomed-out maps whose footprints overflow the box
+    (per-pixel fallback) with pixels mapping outside the source ("far" entries, zero border), and a width/height that
+    leave partial tiles."""
     rows, cols, n = 540 + 16, 720 + 48, 2
     frames = synth.bayer_batch(n, rows, cols, "bayer_gbrg8", 4200, "N")
     kw = dict(FULL); kw["undistort"] = (balance, fov)

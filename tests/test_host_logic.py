@@ -175,6 +175,62 @@ def test_fisheye_new_camera_matrix_and_maps_match_cv2(size, balance, fov):
     assert float(np.abs(m[..., 0] - mx).max()) <= 1e-3 and float(np.abs(m[..., 1] - my).max()) <= 1e-3
 
 
+@pytest.mark.parametrize("size,balance,fov", [((720, 540), 0.0, 0.8), ((768, 556), 0.0, 0.45), ((768, 556), 0.5, 2.5),
+                                              ((1920, 1080), 1.0, 1.2)])
+def test_undistortion_tile_table_and_padded_map(size, balance, fov):
+    """Host products of the tile undistortion kernel (include/rip_b200.h: debug tables): the packed entries are the
+    integers cv::remap derives; the tile table's origin is the footprint's upper-left corner (x floored to 4 pixels); a
+    tile carries the FAST flag exactly when every tap of every pixel lies inside the 176x48 box at that origin and no
+    entry is "far"; padding entries of the tile-padded map point at the edge pixel's source position."""
+    TW, TH, BW, BH = 128, 24, 176, 48
+    w, h = size
+    calib = scaled_calib(w, h)
+    p = RawImagePipeline(False, "", "", "")
+    _setup_undistortion(p, calib, balance, fov)
+    m = np.frombuffer(p.debug_table("undistortion_map"), np.float32).reshape(h, w, 2)
+    packed = np.frombuffer(p.debug_table("undistortion_packed_map", h, w), np.uint32).reshape(h, w)
+    dx = (packed & 0xffff).astype(np.uint16).view(np.int16).astype(np.int64)
+    dy = (packed >> 16).astype(np.uint16).view(np.int16).astype(np.int64)
+    far = dx == -32768
+    xs, ys = np.meshgrid(np.arange(w), np.arange(h))
+    sx = np.rint(m[..., 0].astype(np.float64) * 32).astype(np.int64); sy = np.rint(m[..., 1].astype(np.float64) * 32).astype(np.int64)
+    any_tap = ((sx >> 5) >= -1) & ((sx >> 5) < w) & ((sy >> 5) >= -1) & ((sy >> 5) < h)
+    assert np.array_equal(far, ~any_tap)
+    assert np.array_equal((32 * xs + dx)[~far], sx[~far]) and np.array_equal((32 * ys + dy)[~far], sy[~far])
+
+    tiles_x, tiles_y = -(-w // TW), -(-h // TH)
+    table = np.frombuffer(p.debug_table("undistortion_tile_table", h, w), np.int32).reshape(tiles_y, tiles_x, 4)
+    padded = np.frombuffer(p.debug_table("undistortion_tile_map", h, w), np.uint32).reshape(tiles_y * TH, tiles_x * TW)
+    assert np.array_equal(padded[:h, :w], packed)
+    pdx = (padded & 0xffff).astype(np.uint16).view(np.int16).astype(np.int64)
+    pdy = (padded >> 16).astype(np.uint16).view(np.int16).astype(np.int64)
+    pfar = pdx == -32768
+    pxs, pys = np.meshgrid(np.arange(tiles_x * TW), np.arange(tiles_y * TH))
+    psx, psy = 32 * pxs + pdx, 32 * pys + pdy
+    # padding: same source position as the clamped (edge) pixel, or far where the edge pixel is
+    cx, cy = np.minimum(pxs, w - 1), np.minimum(pys, h - 1)
+    assert np.array_equal(pfar, far[cy, cx])
+    assert np.array_equal(psx[~pfar], (32 * xs + dx)[cy, cx][~pfar]) and np.array_equal(psy[~pfar], (32 * ys + dy)[cy, cx][~pfar])
+    n_fast = 0
+    for ty in range(tiles_y):
+        for tx in range(tiles_x):
+            sl = (slice(ty * TH, ty * TH + TH), slice(tx * TW, tx * TW + TW))
+            ok = ~pfar[sl]
+            bx0, by0, flags, _ = table[ty, tx]
+            if not ok.any():
+                assert (bx0, by0, flags) == (0, 0, 0)
+                continue
+            ix, iy = (psx[sl] >> 5)[ok], (psy[sl] >> 5)[ok]
+            assert bx0 == (ix.min() & ~3) and by0 == iy.min()
+            fits = ix.max() + 1 - bx0 <= BW - 1 and iy.max() + 1 - by0 <= BH - 1
+            assert flags == (1 if fits and ok.all() else 0), (tx, ty)
+            n_fast += int(flags)
+    if fov in (0.8, 0.45):
+        assert n_fast == tiles_x * tiles_y  # the example map, also zoomed in 2.2x: every tile takes the test-free path
+    if fov == 2.5:
+        assert n_fast == 0                  # zoomed out 2.5x: footprints overflow the box, corners map outside the source
+
+
 def test_fisheye_new_size_and_1p6mp_calibration_file():
     p = RawImagePipeline(False, "", os.path.join(CONFIG, "alphasense_calib_1.6mp_example.yaml"), "")
     assert (p.get_dist_image_width(), p.get_dist_image_height()) == (1440, 1080)
