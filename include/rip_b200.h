@@ -152,8 +152,12 @@ RIP_API int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_f
  * Host-computed tables exactly as the kernels consume them (no GPU needed): "gamma_lut" (256 B,
  * gamma_correction.cpp:35-42), "enhancer_luts" (768 B), "vignetting_mask" (rows x cols fp32,
  * vignetting_correction.cpp:32-63), "undistortion_map" (dist_h x dist_w interleaved (x, y) fp32,
- * undistortion.cpp:212-220), "ccc_response" (256 x 256 fp64, the convolution part of the last CCC response; needs a
- * processed frame).  `rows`/`cols` are only used by "vignetting_mask".                                        */
+ * undistortion.cpp:212-220), "undistortion_packed_map" (u32 per output pixel for a rows x cols source image: two
+ * int16 = cvRound(map * 32) relative to the pixel), "undistortion_tile_table" (4 x i32 per 128 x 24 output tile:
+ * footprint origin x, y, flags, 0) and "undistortion_tile_map" (the packed map padded to whole tiles) -- the host-side
+ * inputs of the tile undistortion kernel --, "ccc_response" (256 x 256 fp64, the convolution part of the last CCC
+ * response; needs a processed frame).  `rows`/`cols`: the mask size for "vignetting_mask", the source image size for
+ * the three packed-map tables.                                                                                 */
 RIP_API int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void* out, size_t capacity,
                             size_t* bytes);
 
