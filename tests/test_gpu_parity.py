@@ -304,20 +304,25 @@ def test_two_gpus_from_one_process(oracle_built):
     _, o = make_pair(rows, cols, **FULL)
     refs = [o.apply(f, "bayer_rggb8")[0] for f in frames]
     got = [None, None]
+    errors = []
 
     def worker(dev):
-        p, _ = make_pair(rows, cols, **FULL)
-        p._check(p._lib.rip_set_device(p._h, dev))
-        for _ in range(3):
-            got[dev] = p.process(frames[dev], "bayer_rggb8")
-        batch = p.process_batch(np.stack([frames[dev]] * 3), "bayer_rggb8")
-        assert_same(batch[2], refs[dev], f"batch on device {dev}")
+        try:
+            p, _ = make_pair(rows, cols, **FULL)
+            p._check(p._lib.rip_set_device(p._h, dev))
+            for _ in range(3):
+                got[dev] = p.process(frames[dev], "bayer_rggb8")
+            batch = p.process_batch(np.stack([frames[dev]] * 3), "bayer_rggb8")   # 4-byte intermediate + tile undistortion
+            assert_same(batch[2], refs[dev], f"batch on device {dev}")
+        except BaseException as e:  # an exception in a thread would otherwise be lost
+            errors.append((dev, e))
 
     threads = [threading.Thread(target=worker, args=(d,)) for d in range(2)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
+    assert not errors, errors
     for d in range(2):
         assert got[d] is not None
         assert_same(got[d], refs[d], f"device {d}")
