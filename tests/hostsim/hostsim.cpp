@@ -162,6 +162,22 @@ int hs_remap_bgrx_packed(const uint32_t* src, int rows, int cols, const float* m
   return 1;
 }
 
+// The tile kernel's per-pixel arithmetic (rip_fast.cu k_remap_tile, test-free path) on a host copy of its shared-memory
+// box: taps addressed as row base + dyi * box_w + dxi straight from the packed entry, blended by remap_blend_w.
+// `box` holds box_h x box_w pixels whose upper-left corner is source pixel (bx0, by0); zeros outside the image.
+uint32_t hs_remap_tile_pixel(const uint32_t* box, int box_w, int bx0, int by0, uint32_t packed, int x, int y) {
+  const uint32_t* q = box + ((y - by0) * box_w + (x - bx0)) + (remap_packed_dyi(packed) * box_w + remap_packed_dxi(packed));
+  return remap_blend_w(q[0], q[1], q[box_w], q[box_w + 1], packed & 31u, (packed >> 10) & 0x7c0u);
+}
+uint32_t hs_remap_pack(float mx, float my, int x, int y, int rows, int cols, int* ok) {
+  uint32_t e = 0;
+  *ok = remap_pack_entry(mx, my, x, y, rows, cols, e) ? 1 : 0;
+  return e;
+}
+uint32_t hs_remap_pixel_packed(const uint32_t* src, int rows, int cols, uint32_t packed, int x, int y) {
+  return remap_pixel_bgrx_packed(src, rows, cols, cols, packed, x, y);
+}
+
 void hs_pca_lut(const unsigned long long* stats, uint8_t* lut_b, uint8_t* lut_r, float* coeff) {
   PcaCoeff c = pca_coefficients(stats);
   coeff[0] = c.alpha_b; coeff[1] = c.beta_b; coeff[2] = c.alpha_r; coeff[3] = c.beta_r;

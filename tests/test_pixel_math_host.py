@@ -208,6 +208,41 @@ def test_remap_packed_fixed_point_map_matches_cv2(hostsim):
     assert ok == 0
 
 
+def test_remap_tile_kernel_arithmetic_equals_gather_arithmetic(hostsim):
+    """k_remap_tile's test-free path (address = row base + dyi * box_w + dxi from the packed entry, taps from a zero-padded
+    box, vertical weights x 64, two byte permutes) gives the value of the gather path for every fraction pair (ax, ay),
+    for negative displacements, and at the image border (zeros from the box where the gather drops a tap)."""
+    import ctypes
+    rng = np.random.default_rng(79)
+    rows, cols, BW, BH = 40, 56, 176, 48
+    src = np.zeros((rows, cols, 4), np.uint8); src[..., :3] = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    src32 = src.view(np.uint32).reshape(rows, cols)
+    bx0, by0 = -8, -3                      # a box that sticks out of the image on every side
+    box = np.zeros((BH, BW), np.uint32)
+    box[-by0:-by0 + rows, -bx0:-bx0 + cols] = src32
+    hostsim.hs_remap_tile_pixel.restype = ctypes.c_uint32
+    hostsim.hs_remap_pack.restype = ctypes.c_uint32
+    hostsim.hs_remap_pixel_packed.restype = ctypes.c_uint32
+    ok = ctypes.c_int()
+    n = 0
+    for y in (0, 5, 17):
+        for x in (0, 3, 30):
+            for fy in range(32):
+                for fx in range(32):
+                    # source positions from just outside the upper-left corner to just outside the lower-right one
+                    for base_x, base_y in ((-1.0, -1.0), (4.0, 2.0), (cols - 2.0, rows - 2.0), (cols - 1.0, rows - 1.0), (20.0, 0.0)):
+                        mx, my = base_x + fx / 32.0, base_y + fy / 32.0
+                        e = hostsim.hs_remap_pack(ctypes.c_float(mx), ctypes.c_float(my), x, y, rows, cols, ctypes.byref(ok))
+                        assert ok.value == 1
+                        if (e & 0xffff) == 0x8000:
+                            continue       # "far": the tile is not flagged, the kernel's tested path handles it
+                        a = hostsim.hs_remap_tile_pixel(P(box.ctypes.data), BW, bx0, by0, ctypes.c_uint32(e), x, y)
+                        b = hostsim.hs_remap_pixel_packed(P(src32.ctypes.data), rows, cols, ctypes.c_uint32(e), x, y)
+                        assert a == b, (x, y, mx, my, hex(a), hex(b))
+                        n += 1
+    assert n > 40000
+
+
 def test_remap_identity_is_exact():
     """cv::remap with an identity map returns the image (guards the 32768-weight corner)."""
     rng = np.random.default_rng(9)
