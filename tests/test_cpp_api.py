@@ -71,3 +71,29 @@ def test_cpp_class_cv_mat_branch_compiles_and_runs_host_side(cvmat_exe):
 def test_cpp_class_cv_mat_branch_on_gpu(cvmat_exe):
     out = subprocess.run([cvmat_exe, "gpu"], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), (out.returncode, out.stdout, out.stderr)
+
+
+@pytest.fixture(scope="module")
+def ros_compat_exe():
+    exe = os.path.join(ROOT, "tests", "cpp", "_test_ros_caller_compat")
+    src = os.path.join(ROOT, "tests", "cpp", "test_ros_caller_compat.cpp")
+    deps = [src, os.path.join(ROOT, "include", "raw_image_pipeline", "raw_image_pipeline.hpp"),
+            os.path.join(ROOT, "tests", "cpp", "fake_opencv", "opencv2", "core.hpp"), os.path.join(PKG, "librip_b200.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "tests", "cpp", "fake_opencv"),
+                               "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", PKG, "-lrip_b200", "-Wl,-rpath," + PKG])
+    return exe
+
+
+def test_every_call_of_the_reference_ros_wrapper_compiles_and_runs_host_side(ros_compat_exe):
+    """the calls raw_image_pipeline_ros.cpp:52-291 makes (parameter setters, calibration loaders, CameraInfo
+    getters, image getters), with its argument types, against the drop-in header."""
+    for args in (["host", os.path.join(PKG, "config")], ["host"]):
+        out = subprocess.run([ros_compat_exe] + args, capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.strip().endswith("OK"), (args, out.returncode, out.stdout, out.stderr)
+
+
+@pytest.mark.gpu
+def test_reference_ros_wrapper_call_sequence_on_gpu(ros_compat_exe):
+    out = subprocess.run([ros_compat_exe, "gpu", os.path.join(PKG, "config")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), (out.returncode, out.stdout, out.stderr)
