@@ -15,6 +15,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no librip_b200.so (built artefacts are git-ignored): build it once (nvcc cross-compiles without
+    a GPU).  The package itself never builds or falls back on its own -- it raises when the library is missing."""
+    lib = os.path.join(ROOT, "raw_image_pipeline_b200", "librip_b200.so")
+    if not os.path.exists(lib):
+        subprocess.check_call([sys.executable, "-m", "raw_image_pipeline_b200.build"], cwd=ROOT)
+
+
 def _cuda_available():
     try:
         import torch
