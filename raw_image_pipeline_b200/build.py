@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librip_b200.so")
-SOURCES = ["rip_api.cu", "rip_kernels.cu", "rip_fast.cu", "ccc.cu", "host_state.cpp"]
-HEADERS = ["pixel_math.cuh", "frame_math.cuh", "chain_tables.hpp", "kernels.hpp", "host_state.hpp", "ccc.hpp", "ccc_math.cuh", "devbuf.hpp",
+SOURCES = ["rip_api.cu", "rip_kernels.cu", "rip_fast.cu", "rip_strip.cu", "rip_strip_bgr8.cu", "ccc.cu", "host_state.cpp"]
+HEADERS = ["pixel_math.cuh", "frame_math.cuh", "chain_tables.hpp", "kernels.hpp", "host_state.hpp", "ccc.hpp", "ccc_math.cuh", "devbuf.hpp", "tma.cuh", "bayer_window.cuh", "chain_quad.cuh", "rip_strip.cuh",
            "cv_tables.inc", os.path.join("..", "..", "include", "rip_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,202 @@
+// The chain after debayer+flip (raw_image_pipeline.hpp:151-166) for the four pixels a lane of the strip kernel owns, in
+// the form with the fewest issued instructions.  Same results as pixel_math.cuh chain_pixel() -- which is what the generic
+// kernels run and what tests/test_pixel_math_host.py checks exhaustively against cv2; tests/test_chain_quad_host.py checks
+// this file against chain_pixel() over the whole 2^24 colour cube for every stage set.
+//
+// What differs from chain_pixel():
+//   * inputs stay packed (byte k of Bw/Gw/Rw = pixel k); a channel that needs no table (no white balance, or the G
+//     channel under pca) becomes the float 2^23 + v with ONE byte permute, and the colour-calibration products are
+//     fma(2^23 + v, M, -2^23 M) == RN(v M): exact, one rounding, no int->float conversion;
+//   * white-balance tables are bytes (their entries are 0..255), a quarter of the bank conflicts of the float form;
+//   * a zero bias is skipped (adding +0.0f changes nothing that survives the u8 conversion);
+//   * float(L) is built as (v >> 15) | 0x4B000000 by one funnel shift;
+//   * LabToYF entries carry the constants of abToXZ_b ({y | (ify - 4194) << 16, ify + 10484});
+//   * sdiv[v] and the value-gain float share one 64-bit entry; 3-input min/max;
+//   * HSV2BGR's four candidates are gathered with three byte permutes (the hue entry's selector indexes {t0 t1 . . t2 t3}).
+#pragma once
+#include "pixel_math.cuh"
+
+namespace rip {
+
+struct alignas(8) Pair32 { uint32_t x, y; };  // one 64-bit shared-memory load
+
+// Table addresses.  On the device they are 32-bit shared-window addresses and every lookup is an explicit ld.shared, so
+// that the address arithmetic is exactly what is written here (the compiler otherwise adds the window base with a
+// separate instruction per lookup): a byte index is merged into a 256-byte aligned base by the byte permute that extracts
+// it, a masked index is OR-ed into a 4096-byte aligned base by the same LOP3 that masks it.  On the host (test build)
+// they are byte pointers.
+#if defined(__CUDA_ARCH__)
+typedef uint32_t taddr;
+RIP_HD uint32_t lds_u8(taddr a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+RIP_HD uint32_t lds_u16(taddr a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+RIP_HD uint32_t lds_u32(taddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+RIP_HD Pair32 lds_u64(taddr a) { Pair32 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+// base + byte K of w; base % 256 == 0
+template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return prmt(w, base, 0x7650u + K); }
+// base + (v & mask); base % 4096 == 0, mask < 4096
+RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return (v & mask) | base; }
+#else
+typedef const uint8_t* taddr;
+RIP_HD uint32_t lds_u8(taddr a) { return *a; }
+RIP_HD uint32_t lds_u16(taddr a) { uint16_t v; memcpy(&v, a, 2); return v; }
+RIP_HD uint32_t lds_u32(taddr a) { uint32_t v; memcpy(&v, a, 4); return v; }
+RIP_HD Pair32 lds_u64(taddr a) { Pair32 v; memcpy(&v, a, 8); return v; }
+template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return base + ((w >> (8 * K)) & 255u); }
+RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return base + (v & mask); }
+#endif
+
+// tables of the strip kernel (chain_tables.hpp build_strip_blob lays them out)
+struct StripTables {
+  taddr wb_b, wb_g, wb_r;  // u8[256] each, 256-byte aligned: per-frame white-balance LUTs
+  taddr gamma;             // u8[256]
+  taddr inv_g;             // u8[4096]  sRGBInvGammaTab_b
+  taddr g2;                // u16[256]  sRGBGammaTab_b[gamma[x]]
+  taddr lab_c;             // u16[2048] LabCbrtTab_b, 4096-byte aligned
+  taddr yf2;               // {u32,u32}[256]  x = y | (ify - 4194) << 16 (signed high half), y = ify + 10484
+  taddr sv;                // {u32,u32}[256]  x = sdiv[v], y = float bits of (value gain lut)[v] * (1/255f)
+  taddr hdiv;              // i32[256]
+  taddr hue;               // HueEntry[288], selector for prmt({t0 t1 0 0}, {t2 t3 0 0})
+  taddr sf;                // f32[256]
+};
+
+RIP_HD float bits_to_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+RIP_HD int max3i(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+  return __vimax3_s32(a, b, c);
+#else
+  const int m = a > b ? a : b; return m > c ? m : c;
+#endif
+}
+RIP_HD int min3i(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+  return __vimin3_s32(a, b, c);
+#else
+  const int m = a < b ? a : b; return m < c ? m : c;
+#endif
+}
+RIP_HD uint32_t funnel_shift_r(uint32_t lo, uint32_t hi, int shift) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, shift);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> shift);
+#endif
+}
+
+// float 2^23 + byte K of `w` (exact): bytes {w.K, 00, 00, 4B}
+template <int K>
+RIP_HD float biased_float_of_byte(uint32_t w) { return bits_to_float(prmt(w, 0x4B000000u, 0x7650u + K)); }
+RIP_HD float biased_float_of_u8(uint32_t v) { return bits_to_float(v | 0x4B000000u); }
+
+// RN((x - 2^23) * m) for x = 2^23 + integer: the product is exact inside the fma, so this is the separately rounded
+// product cv::gemm computes (color_calibration.cpp:91-104).  `nm` = -2^23 * m (exact, host-computed).
+RIP_HD float biased_mul(float x, float m, float nm) { return RIP_FMA(x, m, nm); }
+
+// TAIL: the pixel lies in cv2's scalar row tail of HSV2BGR (columns >= width & ~31), which rounds where the vector loop
+// truncates (pixel_math.cuh hsv_gain_to_bgr)
+// WBG: the G channel has a white-balance table too (ccc; pca leaves G untouched).  BIAS: the colour calibration has a
+// non-zero bias (the strip kernel leaves such configurations to the tile kernel, so its instantiations carry no bias add).
+template <uint32_t STAGES, int K, bool TAIL = false, bool WBG = true, bool BIAS = true>
+RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, const ChainConsts& k, const StripTables& t) {
+  int b, g, r;
+  if (STAGES & ST_CC) {
+    float xb, xg, xr;  // 2^23 + channel value
+    if (STAGES & ST_WB) {  // white_balance.cpp:117-127 (pca) / ccc.cpp:383-386: per-frame byte LUTs
+      xb = biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_b, Bw)));
+      xr = biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_r, Rw)));
+      xg = WBG ? biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_g, Gw))) : biased_float_of_byte<K>(Gw);
+    } else {
+      xb = biased_float_of_byte<K>(Bw); xg = biased_float_of_byte<K>(Gw); xr = biased_float_of_byte<K>(Rw);
+    }
+    float y[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float t0 = biased_mul(xb, k.cc[3 * j + 0], k.ccn[3 * j + 0]);
+      const float t1 = biased_mul(xg, k.cc[3 * j + 1], k.ccn[3 * j + 1]);
+      const float t2 = biased_mul(xr, k.cc[3 * j + 2], k.ccn[3 * j + 2]);
+      y[j] = RIP_FADD(RIP_FADD(t0, t1), t2);
+    }
+    if (BIAS) {  // cv::add with the bias Scalar
+      y[0] = RIP_FADD(y[0], k.cc_bias[0]); y[1] = RIP_FADD(y[1], k.cc_bias[1]); y[2] = RIP_FADD(y[2], k.cc_bias[2]);
+    }
+    b = sat_u8_rint(y[0]); g = sat_u8_rint(y[1]); r = sat_u8_rint(y[2]);
+  } else {
+    if (STAGES & ST_WB) {
+      b = (int)lds_u8(taddr_byte<K>(t.wb_b, Bw)); r = (int)lds_u8(taddr_byte<K>(t.wb_r, Rw));
+      g = WBG ? (int)lds_u8(taddr_byte<K>(t.wb_g, Gw)) : (int)prmt(Gw, 0u, 0x4440u + K);
+    } else {
+      b = (int)prmt(Bw, 0u, 0x4440u + K); g = (int)prmt(Gw, 0u, 0x4440u + K); r = (int)prmt(Rw, 0u, 0x4440u + K);
+    }
+  }
+  if (STAGES & ST_VIG) {  // vignetting_correction.cpp:68-93; gamma (if enabled) is folded into t.g2
+    const int R_ = (int)lds_u16(t.g2 + r + r), G_ = (int)lds_u16(t.g2 + g + g), B_ = (int)lds_u16(t.g2 + b + b);
+    // LabCbrtTab_b[(dot + 2048) >> 12]: byte offset 2 * index = (dot >> 11) & 0x1ffe (dot < 2^24)
+    const int fX = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 1777 + G_ * 1541 + B_ * 778 + 2048) >> 11, 0x1ffeu));
+    const int fY = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 871 + G_ * 2929 + B_ * 296 + 2048) >> 11, 0x1ffeu));
+    const int fZ = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 73 + G_ * 448 + B_ * 3575 + 2048) >> 11, 0x1ffeu));
+    // L = (296 fY - 1336934 + 16384) >> 15 lies in 0..255 for every 8-bit input (tests/test_pixel_math_host.py), so
+    // (v >> 15) | 0x4B000000 is the float 2^23 + L
+    const float xL = bits_to_float(funnel_shift_r((uint32_t)(296 * fY - 1320550), 0x2580u, 15));
+    const int Lp = sat_u8_rint(RIP_FMUL(RIP_FSUB(xL, 8388608.0f), mask));
+    const int A = (500 * (fX - fY) + 4210688) >> 15;   // 128 * 32768 + 16384
+    const int B = (200 * (fY - fZ) + 4210688) >> 15;
+    const Pair32 yf = lds_u64(t.yf2 + 8 * Lp);
+    const int yy = (int)(yf.x & 0xffffu);
+    const int fx = ((int)yf.x >> 16) + ((A * 268435 + 128) >> 13);
+    const int fz = (int)yf.y - ((B * 41943 + 16) >> 9);
+    int x = lab_xz_cubic(fx), z = lab_xz_cubic(fz);
+    if ((fx < fz ? fx : fz) <= 3390) {  // dark pixels only
+      if (fx <= 3390) x = lab_xz_linear(fx);
+      if (fz <= 3390) z = lab_xz_linear(fz);
+    }
+    int ro = (12615 * x - 6296 * yy - 2223 * z + 8192) >> 14;
+    int go = (-3773 * x + 7684 * yy + 185 * z + 8192) >> 14;
+    int bo = (217 * x - 836 * yy + 4715 * z + 8192) >> 14;
+    ro = ro < 0 ? 0 : (ro > 4095 ? 4095 : ro);
+    go = go < 0 ? 0 : (go > 4095 ? 4095 : go);
+    bo = bo < 0 ? 0 : (bo > 4095 ? 4095 : bo);
+    r = (int)lds_u8(t.inv_g + ro); g = (int)lds_u8(t.inv_g + go); b = (int)lds_u8(t.inv_g + bo);
+  } else if (STAGES & ST_GAMMA) {  // gamma_correction.cpp:54-56 cv::LUT
+    b = (int)lds_u8(t.gamma + b); g = (int)lds_u8(t.gamma + g); r = (int)lds_u8(t.gamma + r);
+  }
+  if (STAGES & ST_ENH) {  // color_enhancer.cpp:38-47
+    const int vmax = max3i(b, g, r), vmin = min3i(b, g, r);
+    const int d = vmax - vmin;
+    const Pair32 sv = lds_u64(t.sv + 8 * vmax);
+    const int s = (d * (int)sv.x + 2048) >> 12;
+    int hh = r - g + 4 * d;
+    if (vmax == g) hh = b - r + 2 * d;
+    if (vmax == r) hh = g - b;
+    const int h = (hh * (int)lds_u32(t.hdiv + 4 * d) + 2048) >> 12;  // -30 .. 150, wrapped by the table
+    const Pair32 he = lds_u64(t.hue + 8 * (h + HUE_BIAS));             // HueEntry {f, sel}
+    const float f = bits_to_float(he.x), sf = bits_to_float(lds_u32(t.sf + 4 * s)), vf = bits_to_float(sv.y);
+    const float t1 = RIP_FMUL(vf, RIP_FSUB(1.0f, sf));
+    const float t2 = RIP_FMUL(vf, RIP_FMA(-sf, f, 1.0f));
+    const float t3 = RIP_FMUL(vf, RIP_FMA(-sf, RIP_FSUB(1.0f, f), 1.0f));
+    const float c0 = RIP_FMUL(vf, 255.0f), c1 = RIP_FMUL(t1, 255.0f), c2 = RIP_FMUL(t2, 255.0f), c3 = RIP_FMUL(t3, 255.0f);
+    uint32_t m0, m1, m2, m3;
+    if (TAIL) {
+      m0 = (uint32_t)sat_u8_rint(c0); m1 = (uint32_t)sat_u8_rint(c1); m2 = (uint32_t)sat_u8_rint(c2); m3 = (uint32_t)sat_u8_rint(c3);
+    } else {
+      m0 = trunc_u8_word(c0); m1 = trunc_u8_word(c1); m2 = trunc_u8_word(c2); m3 = trunc_u8_word(c3);
+    }
+    // truncated words are 0x4B0000vv on the device (vv on the host), rounded ones are vv: byte 1 is a zero either way
+    return prmt(prmt(m0, m1, 0x1140u), prmt(m2, m3, 0x1140u), he.y);
+  }
+  return pack_bgr(b, g, r);
+}
+
+template <uint32_t STAGES, bool WBG = true, bool BIAS = true>
+RIP_HD void chain_quad(uint32_t Bw, uint32_t Gw, uint32_t Rw, const float m[4], const ChainConsts& k, const StripTables& t, uint32_t px[4]) {
+  px[0] = chain_px<STAGES, 0, false, WBG, BIAS>(Bw, Gw, Rw, m[0], k, t);
+  px[1] = chain_px<STAGES, 1, false, WBG, BIAS>(Bw, Gw, Rw, m[1], k, t);
+  px[2] = chain_px<STAGES, 2, false, WBG, BIAS>(Bw, Gw, Rw, m[2], k, t);
+  px[3] = chain_px<STAGES, 3, false, WBG, BIAS>(Bw, Gw, Rw, m[3], k, t);
+}
+
+}  // namespace rip

@@ -94,6 +94,54 @@ inline void build_chain_blob(const ChainTableParams& q, uint8_t* blob) {
   }
 }
 
+// ---- tables of the strip kernel (chain_quad.cuh StripTables) ---------------------------------------------------
+// Byte offsets; the kernel copies the blob verbatim into 4096-byte aligned shared memory, and chain_quad.cuh relies on
+// SOFF_LABC % 4096 == 0 and SOFF_WB % 256 == 0.  The SOFF_WB region is a hole in the blob: per-frame data.
+enum : int {
+  SOFF_LABC = 0,        // u16[2048]
+  SOFF_INVG = 4096,     // u8[4096]
+  SOFF_WB = 8192,       // u8[3][256]      per-frame white-balance LUTs B, G, R (filled by the kernel)
+  SOFF_GAMMA = 8960,    // u8[256]
+  SOFF_G2 = 9216,       // u16[256]
+  SOFF_YF2 = 9728,      // {u32, u32}[256]  x = y | (ify - 4194) << 16, y = ify + 10484
+  SOFF_SV = 11776,      // {u32, u32}[256]  x = sdiv[v], y = float bits of the value-gain entry
+  SOFF_HDIV = 13824,    // i32[256]
+  SOFF_HUE = 14848,     // HueEntry[288], selector over {t0 t1 0 0 | t2 t3 0 0}
+  SOFF_SF = 17152,      // f32[256]
+  STRIP_TABLE_BYTES = 18176
+};
+
+// `blob`: the legacy blob of the same parameters (build_chain_blob)
+inline void build_strip_blob(const uint8_t* blob, uint8_t* sblob) {
+  memset(sblob, 0, STRIP_TABLE_BYTES);
+  memcpy(sblob + SOFF_GAMMA, blob + OFF_GAMMA, 256);
+  memcpy(sblob + SOFF_INVG, blob + OFF_INVG, 4096);
+  memcpy(sblob + SOFF_G2, blob + OFF_G2, 512);
+  memcpy(sblob + SOFF_LABC, blob + OFF_LABC, 4096);
+  const uint32_t* yf = reinterpret_cast<const uint32_t*>(blob + OFF_YF);
+  uint32_t* yf2 = reinterpret_cast<uint32_t*>(sblob + SOFF_YF2);
+  for (int i = 0; i < 256; ++i) {
+    const int y = (int)(yf[i] & 0xffffu), ify = (int)(yf[i] >> 16);
+    yf2[2 * i] = (uint32_t)y | ((uint32_t)(uint16_t)(int16_t)(ify - 4194) << 16);  // fx = ify + adiv, adiv = (..) - 4194
+    yf2[2 * i + 1] = (uint32_t)(ify + 10484);                                       // fz = ify - bdiv, bdiv = (..) - 10485 + 1
+  }
+  const int32_t* sdiv = reinterpret_cast<const int32_t*>(blob + OFF_SDIV);
+  const uint32_t* vf = reinterpret_cast<const uint32_t*>(blob + OFF_VF);
+  uint32_t* sv = reinterpret_cast<uint32_t*>(sblob + SOFF_SV);
+  for (int i = 0; i < 256; ++i) { sv[2 * i] = (uint32_t)sdiv[i]; sv[2 * i + 1] = vf[i]; }
+  memcpy(sblob + SOFF_HDIV, blob + OFF_HDIV, 1024);
+  const HueEntry* hue = reinterpret_cast<const HueEntry*>(blob + OFF_HUE);
+  HueEntry* hue2 = reinterpret_cast<HueEntry*>(sblob + SOFF_HUE);
+  for (int i = 0; i < 256 + HUE_BIAS; ++i) {
+    // legacy selector nibbles index bytes {t0 t1 t2 t3} (4 = a zero byte); here the candidates sit in {t0 t1 0 0 | t2 t3 0 0}
+    static const uint32_t remap[8] = {0, 1, 4, 5, 2, 2, 2, 2};
+    uint32_t sel = 0;
+    for (int n = 0; n < 4; ++n) sel |= remap[(hue[i].sel >> (4 * n)) & 7u] << (4 * n);
+    hue2[i].f = hue[i].f; hue2[i].sel = sel;
+  }
+  memcpy(sblob + SOFF_SF, blob + OFF_SF, 1024);
+}
+
 // pointers into a blob (host memory or shared memory); wbf is set by the caller
 inline
 #if defined(__CUDACC__)
@@ -112,6 +160,31 @@ ChainTables chain_tables_from_blob(const uint8_t* t, const float* wbf) {
   c.hue = reinterpret_cast<const HueEntry*>(t + OFF_HUE);
   c.sf = reinterpret_cast<const float*>(t + OFF_SF);
   c.vf = reinterpret_cast<const float*>(t + OFF_VF);
+  return c;
+}
+
+}  // namespace rip
+
+#include "chain_quad.cuh"
+
+namespace rip {
+
+inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+StripTables strip_tables_at(taddr t) {  // t: address of the blob copy (device: shared-window address, 4096-byte aligned)
+  StripTables c;
+  c.wb_b = t + SOFF_WB; c.wb_g = t + (SOFF_WB + 256); c.wb_r = t + (SOFF_WB + 512);
+  c.gamma = t + SOFF_GAMMA;
+  c.inv_g = t + SOFF_INVG;
+  c.g2 = t + SOFF_G2;
+  c.lab_c = t + SOFF_LABC;
+  c.yf2 = t + SOFF_YF2;
+  c.sv = t + SOFF_SV;
+  c.hdiv = t + SOFF_HDIV;
+  c.hue = t + SOFF_HUE;
+  c.sf = t + SOFF_SF;
   return c;
 }
 

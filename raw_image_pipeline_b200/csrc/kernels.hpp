@@ -23,6 +23,7 @@ struct FrameParams {
   int angle;                  // 0 / 90 / 180 / 270
   int src;                    // SRC_*
   const uint8_t* tables;      // static blob (TABLE_BYTES)
+  const uint8_t* strip_tables;  // the same tables in the strip kernel's layout (STRIP_TABLE_BYTES, chain_tables.hpp)
   const float* wbf;           // n_frames x 3 x 256 per-frame white-balance LUTs (B,G,R) as floats, or null
   const float* vig;           // vignetting mask in INPUT-frame coordinates: rows x cols, entry (y, x) = mask at flip_dest(y, x)
   int vig_pitch;              // floats per mask row (== cols)
@@ -66,6 +67,19 @@ bool fast_out_ok(const FrameParams& p, bool bgrx);
 // bgrx: write 4-byte B,G,R,0 pixels (out_pitch = ocols * 4) -- the intermediate format of launch_remap_bgrx
 cudaError_t launch_fused_fast(uint32_t stages, const FrameParams& p, bool bgrx, int sm_count, cudaStream_t stream, int* launches);
 cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream_t stream, int* launches);
+// Strip kernel (rip_strip.cu): the same fast path with warp-private TMA rings and a sliding-window demosaic.  Applies
+// wherever fast_path_ok() && fast_out_ok() hold; needs p.strip_tables.
+struct StripGeom {
+  int nstrips, ngroups;   // 128-pixel strips per output row; groups of 8 adjacent strips (one CTA unit each)
+  int nseg, seg_h;        // row segments per frame and their height
+  int units_per_frame;
+  long long total_units;
+};
+StripGeom strip_geometry(const FrameParams& p);
+// `wb_has_g_table`: the G channel's white-balance table is not the identity (ccc); `variant`: experiment switch
+bool strip_kernel_ok(uint32_t stages, const FrameParams& p);
+cudaError_t launch_fused_strip(uint32_t stages, bool wb_has_g_table, const FrameParams& p, bool bgrx, int variant, int sm_count,
+                               cudaStream_t stream, int* launches);
 // 1-channel non-Bayer input (mono8 ...): only flip and the gamma LUT apply (the colour modules skip images that do not
 // have 3 channels: white_balance.hpp:50-52, color_calibration.hpp:47-49, color_enhancer.hpp:38-40)
 cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, int* launches);

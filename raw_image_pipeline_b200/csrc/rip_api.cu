@@ -75,6 +75,7 @@ struct rip_pipeline {
   bool profile = false;
   bool force_generic = false;  // "debug/force_generic_kernels": tests run both kernel families
   bool force_float_map = false;  // "debug/force_float_map": undistortion reads the fp32 map even where the packed one exists
+  int fused_kernel = 0;  // "debug/fused_kernel": 0 = strip kernel (rip_strip.cu), 1 = round-1 tile kernel (rip_fast.cu k_fused_fast)
   bool force_gather_remap = false;  // "debug/force_gather_remap": undistortion gathers from global memory even where the tile kernel applies
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
@@ -92,7 +93,7 @@ struct rip_pipeline {
   }
 
   // device-resident parameters
-  DevBuf d_tables; bool tables_valid = false; ChainTableParams tables_key;
+  DevBuf d_tables, d_strip_tables; bool tables_valid = false; ChainTableParams tables_key;
   DevBuf d_vig; int vig_rows = -1, vig_cols = -1, vig_angle = -1, vig_pitch = 0; double vig_par[3] = {0, 0, 0};
   DevBuf d_map; uint64_t map_epoch = 0; int map_w = 0, map_h = 0;
   DevBuf d_tiles, d_tmap; int tmap_pitch = 0;  // tile table and tile-padded copy of the packed map (kernels.hpp remap_tile_table)
@@ -234,6 +235,10 @@ int ensure_tables(rip_pipeline* p) {
   RIP_CUDA(p, cudaDeviceSynchronize());  // nothing in flight may still read the old tables
   RIP_CUDA(p, p->d_tables.reserve(TABLE_BYTES));
   RIP_CUDA(p, cudaMemcpy(p->d_tables.ptr, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice));
+  std::vector<uint8_t> sblob(STRIP_TABLE_BYTES, 0);
+  build_strip_blob(blob.data(), sblob.data());
+  RIP_CUDA(p, p->d_strip_tables.reserve(STRIP_TABLE_BYTES));
+  RIP_CUDA(p, cudaMemcpy(p->d_strip_tables.ptr, sblob.data(), STRIP_TABLE_BYTES, cudaMemcpyHostToDevice));
   p->tables_valid = true; p->tables_key = key;
   return RIP_OK;
 }
@@ -352,10 +357,12 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   fp.rows = g.rows; fp.cols = g.cols; fp.orows = g.frows; fp.ocols = g.fcols; fp.n_frames = n;
   fp.cfa = g.cfa; fp.angle = g.angle; fp.src = g.src;
   fp.tables = p->d_tables.as<uint8_t>();
+  fp.strip_tables = p->d_strip_tables.as<uint8_t>();
   fp.vig = p->d_vig.as<float>(); fp.vig_pitch = p->vig_pitch;
   for (int i = 0; i < 9; ++i) fp.k.cc[i] = q.cc_matrix[i];
   for (int i = 0; i < 3; ++i) fp.k.cc_bias[i] = (float)q.cc_bias[i];  // Scalar double -> fp32 on cv::add
   fp.k.wb_g_identity = 0;
+  chain_consts_finish(fp.k);
   const bool fast_in = !p->force_generic && fast_path_ok(fp);
   const bool bgrx = undistort && !d_color_user && !keep_bgr_color && fast_in;
   const int och = g.color ? 3 : 1;
@@ -392,7 +399,12 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   }
   RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
   if (!g.color) RIP_CUDA(p, launch_mono(fp, (stages & ST_GAMMA) != 0, stream, &launches));
-  else if (fast_in && fast_out_ok(fp, bgrx)) RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));
+  else if (fast_in && fast_out_ok(fp, bgrx)) {
+    if (p->fused_kernel == 1 || !strip_kernel_ok(stages, fp))
+      RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));  // tile kernel (round 1)
+    else
+      RIP_CUDA(p, launch_fused_strip(stages, wb_kind == 2, fp, bgrx, p->fused_kernel, p->sm_count, stream, &launches));
+  }
   else if (bgrx) return p->fail(RIP_ERR_CUDA, "internal: 4-byte intermediate needs the fast path");
   else RIP_CUDA(p, launch_fused(stages, fp, p->sm_count, stream, &launches));
   RIP_CUDA(p, p->span_end(stream));
@@ -439,6 +451,7 @@ int create_common(int use_gpu, rip_pipeline** out, rip_pipeline*& p) {
   p = new rip_pipeline();
   p->hs.p.use_gpu = use_gpu != 0;
   p->hs.config_dir = default_config_dir();
+  if (const char* v = getenv("RIP_B200_FUSED_KERNEL")) p->fused_kernel = atoi(v);  // experiment switch, see "debug/fused_kernel"
   std::string err;
   if (!ccc_load_model(p->ccc, p->hs.config_dir + "/ccc_model.bin", err)) p->hs.log += "Warning: " + err + "\n";
   *out = p;
@@ -485,7 +498,7 @@ void rip_destroy(rip_pipeline* p) {
   if (p->cuda_ready) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    p->d_tables.release(); p->d_vig.release(); p->d_map.release(); p->d_pmap.release();
+    p->d_tables.release(); p->d_strip_tables.release(); p->d_vig.release(); p->d_map.release(); p->d_pmap.release();
     p->d_in.release(); p->d_out.release(); p->d_tmp.release(); p->scratch.release();
     ccc_release(p->ccc);
     for (Slot& s : p->slots) {
@@ -533,6 +546,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
 
 int rip_set_int(rip_pipeline* p, const char* key, int value) {
   if (key_is(key, "flip/angle")) p->hs.p.flip_angle = value;
+  else if (key_is(key, "debug/fused_kernel")) p->fused_kernel = value;
   else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown int key: ") + key);
   return RIP_OK;
 }

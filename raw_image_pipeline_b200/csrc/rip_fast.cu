@@ -18,8 +18,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "bayer_window.cuh"
 #include "frame_math.cuh"
 #include "kernels.hpp"
+#include "tma.cuh"
 
 namespace rip {
 
@@ -48,47 +50,6 @@ struct FastSmem {
   alignas(16) float wbf[768];
   alignas(8) unsigned long long mbar[2];
 };
-
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.b32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // Tiles are enumerated on a grid anchored at the origin of the OUTPUT frame (TMA stores do not take negative
 // coordinates; loads do, with zero fill).  (x0, y0) is the tile's origin in the INPUT frame: equal to the output
@@ -158,47 +119,6 @@ __device__ __forceinline__ void quad_bgr_words(const uint32_t* s_in, int rows, i
     const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
     Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix);
   }
-}
-
-// ---- vertical sliding window over one 4-pixel column of the staged tile ------------------------------
-// A thread that walks consecutive rows reuses everything a row contributes to its neighbours: per Bayer row the
-// three packed words (centre / shifted left / shifted right) and, in 16-bit lanes, what the rows above and below
-// need from it (A, S) and what it needs from itself (W).  Per output row that leaves 3 shared-memory loads, 2 funnel
-// shifts and 5 byte permutes instead of 9 / 6 / 8 (frame_math.cuh demosaic_quad_swar is the reference form).
-struct BayerRow {
-  uint32_t c, l, r;  // columns x..x+3, x-1..x+2, x+1..x+4
-  uint32_t A;        // centre word, lanes at the colour sites of the rows above / below
-  uint32_t S;        // left + right words, same lanes (their diagonal contribution)
-  uint32_t W;        // left + right words, lanes at this row's own colour sites, + rounding constant
-};
-// `img_row`: row index in the frame (decides the CFA phase); `srow`: row index in the staged tile
-__device__ __forceinline__ BayerRow load_bayer_row(const uint32_t* s_in, int srow, int lane, int img_row, int cfa) {
-  const uint32_t* p = s_in + srow * IN_WORDS + IN_X_WORD0 + lane;
-  const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-  BayerRow b;
-  b.c = w1; b.l = funnel_r(w0, w1, 24); b.r = funnel_r(w1, w2, 8);
-  const uint32_t cpar = (uint32_t)((cfa ^ (cfa >> 1) ^ img_row) & 1);  // column parity of this row's colour sites
-  const uint32_t own = 0x4240u + 0x0101u * cpar, other = 0x4341u - 0x0101u * cpar;
-  b.A = prmt(b.c, 0u, other);
-  b.S = prmt(b.l, 0u, other) + prmt(b.r, 0u, other);
-  b.W = prmt(b.l, 0u, own) + prmt(b.r, 0u, own) + 0x00020002u;
-  return b;
-}
-// packed B / G / R of the row `m` (frame row img_row) between rows `n` (above) and `s` (below)
-__device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRow& m, const BayerRow& s, int img_row, int cfa,
-                                                uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
-  const int cpar = (cfa ^ (cfa >> 1) ^ img_row) & 1;
-  const bool row_has_r = (((img_row ^ (cfa >> 1)) & 1) == 0);
-  const uint32_t H = avg_round_u8x4(m.l, m.r), V = avg_round_u8x4(n.c, s.c);
-  const uint32_t X = ((n.A + s.A + m.W) >> 2) & 0x00ff00ffu;
-  const uint32_t D = ((n.S + s.S + 0x00020002u) >> 2) & 0x00ff00ffu;
-  const uint32_t sel = 0x7250u - 0x4c4cu * (uint32_t)cpar;
-  const uint32_t site = 0x00ff00ffu << (8 * cpar);
-  Gw = prmt(X, m.c, sel);
-  const uint32_t row_colour = (m.c & site) | (H & ~site);
-  const uint32_t other_colour = prmt(D, V, sel);
-  Rw = row_has_r ? row_colour : other_colour;
-  Bw = row_has_r ? other_colour : row_colour;
 }
 
 // the same quad straight from global memory (edge tiles only, see k_fused_fast)
@@ -415,13 +335,13 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
     constexpr int RPW = TH_STATS / 8;
     const int ya = max(c.y0 + RPW * warp, 1), yb = min(c.y0 + RPW * warp + RPW - 1, P.rows - 2);
     if (x < P.cols && ya <= yb) {
-      BayerRow rn = load_bayer_row(s_in, ya - 1 - c.y0 + 1, lane, ya - 1, P.cfa);
-      BayerRow rm = load_bayer_row(s_in, ya - c.y0 + 1, lane, ya, P.cfa);
+      BayerRow rn = load_bayer_row(s_in + (ya - 1 - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, ya - 1, P.cfa);
+      BayerRow rm = load_bayer_row(s_in + (ya - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, ya, P.cfa);
 #pragma unroll 4
       for (int k = 0; k < RPW; ++k) {
         const int y = ya + k;
         if (y <= yb) {
-          const BayerRow rs = load_bayer_row(s_in, y + 1 - c.y0 + 1, lane, y + 1, P.cfa);
+          const BayerRow rs = load_bayer_row(s_in + (y + 1 - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, y + 1, P.cfa);
           uint32_t Bw, Gw, Rw;
           demosaic_window(rn, rm, rs, y, P.cfa, Bw, Gw, Rw);
           if (x == 0 || x + 4 == P.cols) {  // frame border columns: column 0 <- column 1, column W-1 <- column W-2
@@ -470,9 +390,6 @@ struct RemapTileSmem {
   alignas(8) unsigned long long full[RT_STAGES], empty[RT_STAGES];
 };
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // one pixel of a tile without the FAST flag: shared-memory taps when they are inside the box, else the global gather
 __device__ __noinline__ uint32_t remap_tile_pixel_slow(const RemapParams& P, const uint32_t* box, int bx0, int by0, const uint32_t* src,
@@ -658,6 +575,12 @@ cudaError_t dispatch_fast(uint32_t stages, const FrameParams& p, const CUtensorM
 }
 
 }  // namespace
+
+bool make_tensor_map_3d(CUtensorMap* map, CUtensorMapDataType type, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
+                        cuuint64_t stride1, cuuint64_t stride2, cuuint32_t b0, cuuint32_t b1) {
+  return make_map(map, type, base, d0, d1, d2, stride1, stride2, b0, b1);
+}
+bool tensor_maps_available() { return encode_tiled_fn() != nullptr; }
 
 bool fast_path_ok(const FrameParams& p) {
   if (p.src != SRC_BAYER || !(p.angle == 0 || p.angle == 180)) return false;

@@ -56,7 +56,7 @@ def hostsim():
     so = os.path.join(d, "_hostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
         os.path.join(ROOT, "raw_image_pipeline_b200", "csrc", f)
-        for f in ("pixel_math.cuh", "frame_math.cuh", "cv_tables.inc", "chain_tables.hpp", "ccc_math.cuh")]
+        for f in ("pixel_math.cuh", "frame_math.cuh", "cv_tables.inc", "chain_tables.hpp", "ccc_math.cuh", "chain_quad.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
                                "-x", "c++", srcs[0], "-o", so])

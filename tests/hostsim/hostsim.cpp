@@ -96,6 +96,50 @@ void hs_chain(unsigned stages, long n, int width, const uint8_t* in, const float
   }
 }
 
+// the same chain through the strip kernel's four-pixel form (chain_quad.cuh) and its table layout; n % 4 == 0.
+// `tail` != 0: every pixel is treated as a row-tail pixel of HSV2BGR (the strip kernel's out-of-line variant)
+void hs_chain_quad(unsigned stages, long n, int tail, const uint8_t* in, const float* mask, const float* cc, const float* bias,
+                   const double* enh, const uint8_t* wb, const uint8_t* gamma, uint8_t* out) {
+  const std::vector<uint8_t> blob = make_blob(enh, (stages & ST_GAMMA) ? gamma : nullptr);
+  std::vector<uint8_t> sblob(STRIP_TABLE_BYTES);
+  build_strip_blob(blob.data(), sblob.data());
+  bool g_identity = true;
+  for (int i = 0; i < 256; ++i) g_identity = g_identity && wb[256 + i] == i;
+  memcpy(sblob.data() + SOFF_WB, wb, 768);
+  const StripTables t = strip_tables_at(sblob.data());
+  ChainConsts k;
+  memcpy(k.cc, cc, sizeof k.cc); memcpy(k.cc_bias, bias, sizeof k.cc_bias);
+  k.wb_g_identity = g_identity ? 1 : 0;
+  chain_consts_finish(k);
+  for (long i = 0; i < n; i += 4) {
+    uint32_t Bw = 0, Gw = 0, Rw = 0;
+    float m[4];
+    for (int q = 0; q < 4; ++q) {
+      Bw |= (uint32_t)in[3 * (i + q)] << (8 * q); Gw |= (uint32_t)in[3 * (i + q) + 1] << (8 * q); Rw |= (uint32_t)in[3 * (i + q) + 2] << (8 * q);
+      m[q] = mask ? mask[i + q] : 1.0f;
+    }
+    uint32_t px[4];
+    switch (stages & ST_ALL) {
+    // the strip kernel's instantiations: no G table under pca (identity), no bias add when the bias is zero
+#define RIP_CASE(S) case S: \
+      if (tail) for (int q = 0; q < 4; ++q) px[q] = chain_px<S, 0, true, true, true>(Bw >> (8 * q), Gw >> (8 * q), Rw >> (8 * q), m[q], k, t); \
+      else if (g_identity && !k.has_bias) chain_quad<S, false, false>(Bw, Gw, Rw, m, k, t, px); \
+      else if (!k.has_bias) chain_quad<S, true, false>(Bw, Gw, Rw, m, k, t, px); \
+      else chain_quad<S, true, true>(Bw, Gw, Rw, m, k, t, px); \
+      break;
+      RIP_CASE(0) RIP_CASE(1) RIP_CASE(2) RIP_CASE(3) RIP_CASE(4) RIP_CASE(5) RIP_CASE(6) RIP_CASE(7)
+      RIP_CASE(8) RIP_CASE(9) RIP_CASE(10) RIP_CASE(11) RIP_CASE(12) RIP_CASE(13) RIP_CASE(14) RIP_CASE(15)
+      RIP_CASE(16) RIP_CASE(17) RIP_CASE(18) RIP_CASE(19) RIP_CASE(20) RIP_CASE(21) RIP_CASE(22) RIP_CASE(23)
+      RIP_CASE(24) RIP_CASE(25) RIP_CASE(26) RIP_CASE(27) RIP_CASE(28) RIP_CASE(29) RIP_CASE(30) RIP_CASE(31)
+#undef RIP_CASE
+      default: px[0] = px[1] = px[2] = px[3] = 0;
+    }
+    for (int q = 0; q < 4; ++q) {
+      out[3 * (i + q)] = px[q] & 255; out[3 * (i + q) + 1] = (px[q] >> 8) & 255; out[3 * (i + q) + 2] = (px[q] >> 16) & 255;
+    }
+  }
+}
+
 // mode 0: demosaic_at everywhere; mode 1: demosaic_quad where legal; mode 2: demosaic_quad_swar where legal
 void hs_demosaic(const uint8_t* raw, int rows, int cols, int cfa, int angle, int mode, uint8_t* out) {
   const int orows = (angle == 90 || angle == 270) ? cols : rows;
