@@ -325,6 +325,21 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    # ---- parity of the timed outputs: first and last frame of the step against the cv2 oracle (checker only) ----
+    parity = None
+    if not args.no_parity:
+        step_device()
+        torch.cuda.synchronize()
+        o = make_oracle(rows, cols)
+        nbad, maxd, checked = 0, 0, []
+        for i in sorted({0, n - 1}):
+            ref, _ = o.apply(frames[i], ENC)
+            got = d_out[i].cpu().numpy()
+            d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+            nbad += int(np.count_nonzero(d)); maxd = max(maxd, int(d.max())); checked.append(i)
+        parity = {"frames_checked": len(checked), "frames": checked, "max_abs_diff": maxd, "differing_values": nbad,
+                  "against": "oracle/cv2_oracle.py (cv2 replay of the reference CPU path), device-resident output of the timed step"}
+
     peak, peak_src = hbm_peak()
     n_fused = max(kernel_ms[4 + 2], 1.0)
     fused_ms = kernel_ms[2] / n_fused
@@ -376,6 +391,7 @@ def run_b200(args):
                 "api": "rip_apply_batch_host (pinned host buffers, H2D + kernels + D2H inside the timed region, host wall clock)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "parity": parity,
     }
     if world == 1 and not args.no_cpu_baseline:
         v, cores, dt = time_cpu_reference(rows, cols, args.cpu_frames, 1)
@@ -386,6 +402,8 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["differing_values"] != 0:
+        raise SystemExit("bench.py: the timed outputs differ from the oracle: " + json.dumps(parity))
 
 
 def main():
@@ -401,6 +419,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-witness", action="store_true", help="skip the debayer+gamma-only roofline witness")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed outputs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

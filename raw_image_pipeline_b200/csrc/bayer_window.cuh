@@ -46,5 +46,51 @@ __device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRo
   Bw = row_has_r ? other_colour : row_colour;
 }
 
+// ---- the same with everything that depends on a row's CFA phase precomputed ---------------------------------------
+// Rows alternate between two phases.  A kernel that walks rows computes one BayerPhase for its "even" rows (the rows
+// with the parity of a reference row) once; what odd rows need follows from it at no cost: their lane selectors are the
+// even ones swapped, their site mask the complement, their R/B assignment the opposite -- only the merge selector of odd
+// rows takes a register of its own.  With the row loop unrolled by an even count, no per-row selector arithmetic is left.
+struct BayerPhase {
+  uint32_t own, other;    // 16-bit lane selectors of an even row's own colour sites / of its other columns
+  uint32_t sel_e, sel_o;  // merge selectors with an even / odd row as the centre
+  uint32_t site;          // byte mask of an even row's colour sites
+  bool row_has_r;         // an even row holds R (and G) sites
+};
+__device__ __forceinline__ BayerPhase bayer_phase(int even_row, int cfa) {
+  const uint32_t cpar = (uint32_t)((cfa ^ (cfa >> 1) ^ even_row) & 1);
+  BayerPhase q;
+  q.own = 0x4240u + 0x0101u * cpar; q.other = 0x4341u - 0x0101u * cpar;
+  q.sel_e = 0x7250u - 0x4c4cu * cpar; q.sel_o = 0x2604u + 0x4c4cu * cpar;
+  q.site = 0x00ff00ffu << (8 * cpar);
+  q.row_has_r = (((even_row ^ (cfa >> 1)) & 1) == 0);
+  return q;
+}
+template <bool ODD>
+__device__ __forceinline__ BayerRow load_bayer_row(const uint32_t* p, const BayerPhase& q) {
+  const uint32_t own = ODD ? q.other : q.own, other = ODD ? q.own : q.other;
+  const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+  BayerRow b;
+  b.c = w1; b.l = funnel_r(w0, w1, 24); b.r = funnel_r(w1, w2, 8);
+  b.A = prmt(b.c, 0u, other);
+  b.S = prmt(b.l, 0u, other) + prmt(b.r, 0u, other);
+  b.W = prmt(b.l, 0u, own) + prmt(b.r, 0u, own) + 0x00020002u;
+  return b;
+}
+// ODD: the centre row `m` is an odd row
+template <bool ODD>
+__device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRow& m, const BayerRow& s, const BayerPhase& q,
+                                                uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const uint32_t H = avg_round_u8x4(m.l, m.r), V = avg_round_u8x4(n.c, s.c);
+  const uint32_t X = ((n.A + s.A + m.W) >> 2) & 0x00ff00ffu;
+  const uint32_t D = ((n.S + s.S + 0x00020002u) >> 2) & 0x00ff00ffu;
+  const uint32_t sel = ODD ? q.sel_o : q.sel_e;
+  Gw = prmt(X, m.c, sel);
+  const uint32_t row_colour = ODD ? ((m.c & ~q.site) | (H & q.site)) : ((m.c & q.site) | (H & ~q.site));
+  const uint32_t other_colour = prmt(D, V, sel);
+  const bool row_has_r = ODD ? !q.row_has_r : q.row_has_r;
+  Rw = row_has_r ? row_colour : other_colour;
+  Bw = row_has_r ? other_colour : row_colour;
+}
 
 }  // namespace rip

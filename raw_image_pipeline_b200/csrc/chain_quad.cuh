@@ -5,11 +5,11 @@
 //
 // What differs from chain_pixel():
 //   * inputs stay packed (byte k of Bw/Gw/Rw = pixel k); a channel that needs no table (no white balance, or the G
-//     channel under pca) becomes the float 2^23 + v with ONE byte permute, and the colour-calibration products are
-//     fma(2^23 + v, M, -2^23 M) == RN(v M): exact, one rounding, no int->float conversion;
+//     channel under pca) becomes the float 2^23 + v with ONE byte permute (then one subtraction: no conversion pipe);
 //   * white-balance tables are bytes (their entries are 0..255), a quarter of the bank conflicts of the float form;
 //   * a zero bias is skipped (adding +0.0f changes nothing that survives the u8 conversion);
-//   * float(L) is built as (v >> 15) | 0x4B000000 by one funnel shift;
+//   * float(L) is built as (v >> 15) | 0x4B000000 by one funnel shift; the sRGB table holds 2 G + 1, which makes the
+//     rounding constant of the XYZ descale implicit (matrix rows sum to 4096);
 //   * LabToYF entries carry the constants of abToXZ_b ({y | (ify - 4194) << 16, ify + 10484});
 //   * sdiv[v] and the value-gain float share one 64-bit entry; 3-input min/max;
 //   * HSV2BGR's four candidates are gathered with three byte permutes (the hue entry's selector indexes {t0 t1 . . t2 t3}).
@@ -45,12 +45,23 @@ template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return base +
 RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return base + (v & mask); }
 #endif
 
+#if defined(__CUDACC__)
+// table address of a shared-memory pointer (device code; the host branch only serves nvcc's host pass, which parses kernels)
+__device__ __forceinline__ taddr taddr_of_shared(const void* p) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__cvta_generic_to_shared(p);
+#else
+  return static_cast<const uint8_t*>(p);
+#endif
+}
+#endif
+
 // tables of the strip kernel (chain_tables.hpp build_strip_blob lays them out)
 struct StripTables {
   taddr wb_b, wb_g, wb_r;  // u8[256] each, 256-byte aligned: per-frame white-balance LUTs
   taddr gamma;             // u8[256]
   taddr inv_g;             // u8[4096]  sRGBInvGammaTab_b
-  taddr g2;                // u16[256]  sRGBGammaTab_b[gamma[x]]
+  taddr g2;                // u16[256]  2 * sRGBGammaTab_b[gamma[x]] + 1
   taddr lab_c;             // u16[2048] LabCbrtTab_b, 4096-byte aligned
   taddr yf2;               // {u32,u32}[256]  x = y | (ify - 4194) << 16 (signed high half), y = ify + 10484
   taddr sv;                // {u32,u32}[256]  x = sdiv[v], y = float bits of (value gain lut)[v] * (1/255f)
@@ -93,10 +104,6 @@ template <int K>
 RIP_HD float biased_float_of_byte(uint32_t w) { return bits_to_float(prmt(w, 0x4B000000u, 0x7650u + K)); }
 RIP_HD float biased_float_of_u8(uint32_t v) { return bits_to_float(v | 0x4B000000u); }
 
-// RN((x - 2^23) * m) for x = 2^23 + integer: the product is exact inside the fma, so this is the separately rounded
-// product cv::gemm computes (color_calibration.cpp:91-104).  `nm` = -2^23 * m (exact, host-computed).
-RIP_HD float biased_mul(float x, float m, float nm) { return RIP_FMA(x, m, nm); }
-
 // TAIL: the pixel lies in cv2's scalar row tail of HSV2BGR (columns >= width & ~31), which rounds where the vector loop
 // truncates (pixel_math.cuh hsv_gain_to_bgr)
 // WBG: the G channel has a white-balance table too (ccc; pca leaves G untouched).  BIAS: the colour calibration has a
@@ -113,12 +120,15 @@ RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, cons
     } else {
       xb = biased_float_of_byte<K>(Bw); xg = biased_float_of_byte<K>(Gw); xr = biased_float_of_byte<K>(Rw);
     }
+    // (float)v = (2^23 + v) - 2^23 exactly; the nine matrix entries stay constant-bank operands of the multiplies (a fused
+    // fma(2^23 + v, M, -2^23 M) form saves these three subtractions but needs nine more live registers -- measured: spills)
+    const float fb = RIP_FSUB(xb, 8388608.0f), fg = RIP_FSUB(xg, 8388608.0f), fr = RIP_FSUB(xr, 8388608.0f);
     float y[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float t0 = biased_mul(xb, k.cc[3 * j + 0], k.ccn[3 * j + 0]);
-      const float t1 = biased_mul(xg, k.cc[3 * j + 1], k.ccn[3 * j + 1]);
-      const float t2 = biased_mul(xr, k.cc[3 * j + 2], k.ccn[3 * j + 2]);
+      const float t0 = RIP_FMUL(fb, k.cc[3 * j + 0]);
+      const float t1 = RIP_FMUL(fg, k.cc[3 * j + 1]);
+      const float t2 = RIP_FMUL(fr, k.cc[3 * j + 2]);
       y[j] = RIP_FADD(RIP_FADD(t0, t1), t2);
     }
     if (BIAS) {  // cv::add with the bias Scalar
@@ -134,11 +144,13 @@ RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, cons
     }
   }
   if (STAGES & ST_VIG) {  // vignetting_correction.cpp:68-93; gamma (if enabled) is folded into t.g2
+    // t.g2 holds 2 G + 1 (G = sRGBGammaTab_b entry): every row of the XYZ matrix sums to 4096, so
+    // sum c_i (2 G_i + 1) = 2 (sum c_i G_i + 2048) -- the rounding constant of the descale comes for free, and
+    // LabCbrtTab_b[(dot + 2048) >> 12] sits at byte offset 2 * index = (sum >> 12) & 0x1ffe (sum < 2^25)
     const int R_ = (int)lds_u16(t.g2 + r + r), G_ = (int)lds_u16(t.g2 + g + g), B_ = (int)lds_u16(t.g2 + b + b);
-    // LabCbrtTab_b[(dot + 2048) >> 12]: byte offset 2 * index = (dot >> 11) & 0x1ffe (dot < 2^24)
-    const int fX = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 1777 + G_ * 1541 + B_ * 778 + 2048) >> 11, 0x1ffeu));
-    const int fY = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 871 + G_ * 2929 + B_ * 296 + 2048) >> 11, 0x1ffeu));
-    const int fZ = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 73 + G_ * 448 + B_ * 3575 + 2048) >> 11, 0x1ffeu));
+    const int fX = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 1777 + G_ * 1541 + B_ * 778) >> 12, 0x1ffeu));
+    const int fY = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 871 + G_ * 2929 + B_ * 296) >> 12, 0x1ffeu));
+    const int fZ = (int)lds_u16(taddr_masked(t.lab_c, (uint32_t)(R_ * 73 + G_ * 448 + B_ * 3575) >> 12, 0x1ffeu));
     // L = (296 fY - 1336934 + 16384) >> 15 lies in 0..255 for every 8-bit input (tests/test_pixel_math_host.py), so
     // (v >> 15) | 0x4B000000 is the float 2^23 + L
     const float xL = bits_to_float(funnel_shift_r((uint32_t)(296 * fY - 1320550), 0x2580u, 15));

@@ -102,7 +102,7 @@ enum : int {
   SOFF_INVG = 4096,     // u8[4096]
   SOFF_WB = 8192,       // u8[3][256]      per-frame white-balance LUTs B, G, R (filled by the kernel)
   SOFF_GAMMA = 8960,    // u8[256]
-  SOFF_G2 = 9216,       // u16[256]
+  SOFF_G2 = 9216,       // u16[256]        2 * sRGBGammaTab_b[gamma[x]] + 1
   SOFF_YF2 = 9728,      // {u32, u32}[256]  x = y | (ify - 4194) << 16, y = ify + 10484
   SOFF_SV = 11776,      // {u32, u32}[256]  x = sdiv[v], y = float bits of the value-gain entry
   SOFF_HDIV = 13824,    // i32[256]
@@ -116,7 +116,9 @@ inline void build_strip_blob(const uint8_t* blob, uint8_t* sblob) {
   memset(sblob, 0, STRIP_TABLE_BYTES);
   memcpy(sblob + SOFF_GAMMA, blob + OFF_GAMMA, 256);
   memcpy(sblob + SOFF_INVG, blob + OFF_INVG, 4096);
-  memcpy(sblob + SOFF_G2, blob + OFF_G2, 512);
+  const uint16_t* g2 = reinterpret_cast<const uint16_t*>(blob + OFF_G2);
+  uint16_t* g2s = reinterpret_cast<uint16_t*>(sblob + SOFF_G2);
+  for (int i = 0; i < 256; ++i) g2s[i] = (uint16_t)(2 * g2[i] + 1);  // <= 4081
   memcpy(sblob + SOFF_LABC, blob + OFF_LABC, 4096);
   const uint32_t* yf = reinterpret_cast<const uint32_t*>(blob + OFF_YF);
   uint32_t* yf2 = reinterpret_cast<uint32_t*>(sblob + SOFF_YF2);

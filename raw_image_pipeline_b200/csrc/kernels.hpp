@@ -25,7 +25,7 @@ struct FrameParams {
   const uint8_t* tables;      // static blob (TABLE_BYTES)
   const uint8_t* strip_tables;  // the same tables in the strip kernel's layout (STRIP_TABLE_BYTES, chain_tables.hpp)
   const float* wbf;           // n_frames x 3 x 256 per-frame white-balance LUTs (B,G,R) as floats, or null
-  const float* vig;           // vignetting mask in INPUT-frame coordinates: rows x cols, entry (y, x) = mask at flip_dest(y, x)
+  const float* vig;           // vignetting mask in INPUT-frame coordinates: rows x cols, entry (y, x) = mask at flip_dest(y, x); + 4 rows of padding
   int vig_pitch;              // floats per mask row (== cols)
   ChainConsts k;
   unsigned long long* stats;  // n_frames x 8 (stats kernel only)
@@ -71,19 +71,22 @@ cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream
 // wherever fast_path_ok() && fast_out_ok() hold; needs p.strip_tables.
 struct StripGeom {
   int nstrips, ngroups;   // 128-pixel strips per output row; groups of 8 adjacent strips (one CTA unit each)
-  int nseg, seg_h;        // row segments per frame and their height
+  int nseg, seg_h;        // row segments of the interior rows 1 .. H-2 per frame and their height; + 2 one-row border units
   int units_per_frame;
   long long total_units;
 };
 StripGeom strip_geometry(const FrameParams& p);
 // `wb_has_g_table`: the G channel's white-balance table is not the identity (ccc); `variant`: experiment switch
 bool strip_kernel_ok(uint32_t stages, const FrameParams& p);
+bool strip_kernel_preferred(uint32_t stages);  // the kernel family the default configuration picks for this stage set
 cudaError_t launch_fused_strip(uint32_t stages, bool wb_has_g_table, const FrameParams& p, bool bgrx, int variant, int sm_count,
                                cudaStream_t stream, int* launches);
 // 1-channel non-Bayer input (mono8 ...): only flip and the gamma LUT apply (the colour modules skip images that do not
 // have 3 channels: white_balance.hpp:50-52, color_calibration.hpp:47-49, color_enhancer.hpp:38-40)
 cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, int* launches);
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
+// u8 validity mask of the rectified image: 255 where all four taps of the remap lie inside the rows x cols source
+cudaError_t launch_rect_mask(const float2* map, int orows, int ocols, int rows, int cols, uint8_t* mask, cudaStream_t stream, int* launches);
 // same remap from a 4-byte-per-pixel B,G,R,0 source (p.pitch = cols * 4) to BGR8
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches);
 // tile path of the same (rip_fast.cu): TMA-staged source boxes, needs the packed map and ocols % 4 == 0

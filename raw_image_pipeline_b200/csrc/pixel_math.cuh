@@ -76,12 +76,10 @@ struct ChainConsts {
   float cc[9];      // row-major, channel order B,G,R (Matx33f, color_calibration.cpp:78-79)
   float cc_bias[3];
   int wb_g_identity;  // 1: the G white-balance LUT is the identity (pca): used by the path without colour calibration
-  float ccn[9];     // -2^23 * cc[i] (exact): lets chain_quad.cuh multiply the float 2^23 + v by cc[i] with one fma
   int has_bias;     // 0: every cc_bias is +-0 and the add is skipped (chain_quad.cuh)
 };
 // fills the derived members from cc / cc_bias
 RIP_HD void chain_consts_finish(ChainConsts& k) {
-  for (int i = 0; i < 9; ++i) k.ccn[i] = -8388608.0f * k.cc[i];
   k.has_bias = (k.cc_bias[0] != 0.0f || k.cc_bias[1] != 0.0f || k.cc_bias[2] != 0.0f) ? 1 : 0;  // NaN counts as a bias
 }
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -75,7 +76,8 @@ struct rip_pipeline {
   bool profile = false;
   bool force_generic = false;  // "debug/force_generic_kernels": tests run both kernel families
   bool force_float_map = false;  // "debug/force_float_map": undistortion reads the fp32 map even where the packed one exists
-  int fused_kernel = 0;  // "debug/fused_kernel": 0 = strip kernel (rip_strip.cu), 1 = round-1 tile kernel (rip_fast.cu k_fused_fast)
+  bool emit_rect_mask = false;  // "undistortion/rect_mask": getRectMask() returns a real validity mask (the reference's is always empty)
+  int fused_kernel = 0;  // "debug/fused_kernel": 0 = measured choice per stage set, 1 = tile kernel (rip_fast.cu), >= 2 = strip kernel (rip_strip.cuh)
   bool force_gather_remap = false;  // "debug/force_gather_remap": undistortion gathers from global memory even where the tile kernel applies
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
@@ -110,6 +112,16 @@ struct rip_pipeline {
   float last_pca[4] = {0, 0, 0, 0};
 
   std::vector<Slot> slots;
+  // rip_apply: pinned staging buffers and the captured CUDA graph of the last (shape, configuration)
+  uint8_t* h_stage_in = nullptr; size_t h_stage_in_cap = 0;
+  uint8_t* h_stage_out = nullptr; size_t h_stage_out_cap = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  // rip_apply_batch_device: one scratch set per caller stream, so that calls in flight on different streams never share
+  // white-balance tables / statistics / intermediates (calls on ONE stream are ordered by the stream itself)
+  std::map<cudaStream_t, Scratch> dev_scratch;
+  // batch entry points leave the CCC estimate of their last frame on the device; the stats getters fetch it on demand
+  const DevBuf* ccc_pending_gains = nullptr;
+  cudaStream_t ccc_pending_stream = nullptr;
 
   int fail(int code, const std::string& msg) { last_error = msg; return code; }
   int cuda_fail(cudaError_t e, const char* what) {
@@ -265,6 +277,8 @@ int ensure_vignetting(rip_pipeline* p, int rows, int cols, int angle) {
       full[(size_t)y * cols + x] = quad[(size_t)(std::abs(2 * oy - orows) >> 1) * qc + (std::abs(2 * ox - ocols) >> 1)];
     }
   RIP_CUDA(p, cudaDeviceSynchronize());
+  // four rows of padding (1.0f): the strip kernel reads the mask rows of a whole 4-row chunk even where the frame ends inside it
+  full.resize(full.size() + (size_t)4 * cols, 1.0f);
   RIP_CUDA(p, p->d_vig.reserve(full.size() * sizeof(float)));
   RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, full.data(), full.size() * sizeof(float), cudaMemcpyHostToDevice));
   p->vig_rows = rows; p->vig_cols = cols; p->vig_angle = angle; p->vig_pitch = cols; memcpy(p->vig_par, par, sizeof par);
@@ -400,7 +414,9 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   RIP_CUDA(p, p->span_begin(rip_pipeline::SPAN_FUSED, stream));
   if (!g.color) RIP_CUDA(p, launch_mono(fp, (stages & ST_GAMMA) != 0, stream, &launches));
   else if (fast_in && fast_out_ok(fp, bgrx)) {
-    if (p->fused_kernel == 1 || !strip_kernel_ok(stages, fp))
+    // "debug/fused_kernel": 0 = the measured choice per stage set, 1 = always the tile kernel, >= 2 = always the strip kernel
+    const bool strip = p->fused_kernel == 0 ? strip_kernel_preferred(stages) : p->fused_kernel != 1;
+    if (!strip || !strip_kernel_ok(stages, fp))
       RIP_CUDA(p, launch_fused_fast(stages, fp, bgrx, p->sm_count, stream, &launches));  // tile kernel (round 1)
     else
       RIP_CUDA(p, launch_fused_strip(stages, wb_kind == 2, fp, bgrx, p->fused_kernel, p->sm_count, stream, &launches));
@@ -498,16 +514,19 @@ void rip_destroy(rip_pipeline* p) {
   if (p->cuda_ready) {
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    p->d_tables.release(); p->d_strip_tables.release(); p->d_vig.release(); p->d_map.release(); p->d_pmap.release();
-    p->d_in.release(); p->d_out.release(); p->d_tmp.release(); p->scratch.release();
-    ccc_release(p->ccc);
-    for (Slot& s : p->slots) {
-      s.in.release(); s.out.release(); s.scratch.release();
-      if (s.stream) cudaStreamDestroy(s.stream);
+    for (auto& sp : p->spans) {  // profiling events nobody asked for
+      if (sp.a) cudaEventDestroy(sp.a);
+      if (sp.b) cudaEventDestroy(sp.b);
     }
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->h_stage_in) cudaFreeHost(p->h_stage_in);
+    if (p->h_stage_out) cudaFreeHost(p->h_stage_out);
+    ccc_release(p->ccc);
+    for (Slot& s : p->slots)
+      if (s.stream) cudaStreamDestroy(s.stream);
     if (p->stream) cudaStreamDestroy(p->stream);
   }
-  delete p;
+  delete p;  // every DevBuf frees its memory in its destructor
 }
 
 const char* rip_last_error(const rip_pipeline* p) { return p ? p->last_error.c_str() : g_create_error.c_str(); }
@@ -531,6 +550,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "debug/force_generic_kernels")) p->force_generic = v;
   else if (key_is(key, "debug/force_float_map")) p->force_float_map = v;
   else if (key_is(key, "debug/force_gather_remap")) p->force_gather_remap = v;
+  else if (key_is(key, "undistortion/rect_mask")) p->emit_rect_mask = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;
@@ -619,8 +639,19 @@ int rip_get_bool(rip_pipeline* p, const char* key, int* value) {
   return RIP_OK;
 }
 
+// the CCC estimate a device-batch call left behind (synchronises that call's stream)
+static int ccc_fetch_pending(rip_pipeline* p) {
+  if (!p->ccc_pending_gains) return RIP_OK;
+  int rc = ensure_cuda(p);
+  if (rc != RIP_OK) return rc;
+  rc = ccc_fetch_last(p->ccc, *p->ccc_pending_gains, p->ccc_pending_stream, p->last_error);
+  p->ccc_pending_gains = nullptr;
+  return rc;
+}
+
 int rip_get_int(rip_pipeline* p, const char* key, int* value) {
   const Params& q = p->hs.p;
+  if (key_is(key, "stats/ccc_u") || key_is(key, "stats/ccc_v")) { int rc = ccc_fetch_pending(p); if (rc != RIP_OK) return rc; }
   if (key_is(key, "flip/angle")) *value = q.flip_angle;
   else if (key_is(key, "dist/image_height")) *value = q.dist_h;
   else if (key_is(key, "dist/image_width")) *value = q.dist_w;
@@ -680,6 +711,7 @@ int rip_get_doubles(rip_pipeline* p, const char* key, double* values, int capaci
   else if (key_is(key, "rect/projection_matrix")) from(q.rect_P, 12);
   else if (key_is(key, "stats/pca_coefficients")) { for (float f : p->last_pca) v.push_back((double)f); }
   else if (key_is(key, "stats/kernel_ms")) {
+    if (p->cuda_ready) { int rc = ensure_cuda(p); if (rc != RIP_OK) return rc; }
     // {stats, lut, fused, remap} total milliseconds and span counts since the last query; the
     // caller must have synchronised the stream(s) the work was enqueued on
     v.assign(2 * rip_pipeline::SPAN_KINDS, 0.0);
@@ -693,7 +725,7 @@ int rip_get_doubles(rip_pipeline* p, const char* key, double* values, int capaci
     }
     p->spans.clear();
   }
-  else if (key_is(key, "stats/ccc_gains")) { v = {(double)p->ccc.gain_b, (double)p->ccc.gain_g, (double)p->ccc.gain_r}; }
+  else if (key_is(key, "stats/ccc_gains")) { int rc = ccc_fetch_pending(p); if (rc != RIP_OK) return rc; v = {(double)p->ccc.gain_b, (double)p->ccc.gain_g, (double)p->ccc.gain_r}; }
   else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown doubles key: ") + key);
   if (n) *n = (int)v.size();
   if (!values || capacity < (int)v.size()) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "doubles buffer too small");
@@ -732,6 +764,7 @@ int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void*
     memcpy(data.data(), src, data.size());
   } else if (key_is(name, "ccc_response")) {  // last frame of the last call: 256 x 256 fp64, == cv2 response / 65536 - bias
     if (!p->ccc.d_last_response) return p->fail(RIP_ERR_INVALID_ARGUMENT, "no CCC frame processed yet");
+    { int rc = ensure_cuda(p); if (rc != RIP_OK) return rc; }
     std::vector<double> cplx(2 * 65536);
     RIP_CUDA(p, cudaDeviceSynchronize());
     RIP_CUDA(p, cudaMemcpy(cplx.data(), p->ccc.d_last_response, cplx.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -780,6 +813,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   RIP_CUDA(p, cudaMemcpyAsync(out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
   if (wbk == 1) RIP_CUDA(p, cudaMemcpyAsync(p->last_pca, p->scratch.coeff.ptr, sizeof p->last_pca, cudaMemcpyDeviceToHost, p->stream));
   if (wbk == 2 && (rc = ccc_fetch_last(p->ccc, p->scratch.gains, p->stream, p->last_error)) != RIP_OK) return rc;
+  p->ccc_pending_gains = nullptr;
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
   p->have_frame = true; p->last_geom = g; p->last_in_encoding = encoding;
   memcpy(encoding, g.out_encoding.c_str(), g.out_encoding.size() + 1);
@@ -791,10 +825,25 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
 
 int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity, int* rows, int* cols, int* channels) {
   auto shape = [&](int r, int c, int ch) { if (rows) *rows = r; if (cols) *cols = c; if (channels) *channels = ch; };
-  if (which == RIP_IMAGE_RECT_MASK || !p->have_frame) { shape(0, 0, 0); return RIP_OK; }  // undistortion.hpp:136 never written
+  // undistortion.hpp:136: the reference never writes rect_mask_, getRectMask() is empty.  That stays the default; with
+  // "undistortion/rect_mask" set the mask exists: 255 where the rectified pixel interpolates real pixels only.
+  if (!p->have_frame || (which == RIP_IMAGE_RECT_MASK && !(p->emit_rect_mask && p->last_geom.undistort))) { shape(0, 0, 0); return RIP_OK; }
   const FrameGeom& g = p->last_geom;
   int rc = ensure_cuda(p);
   if (rc != RIP_OK) return rc;
+  if (which == RIP_IMAGE_RECT_MASK) {
+    shape(g.orows, g.ocols, 1);
+    const size_t bytes = (size_t)g.orows * g.ocols;
+    if (!out || out_capacity < bytes) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "image buffer too small");
+    if ((rc = ensure_map(p)) != RIP_OK) return rc;
+    RIP_CUDA(p, p->d_tmp.reserve(bytes));
+    int launches = 0;
+    RIP_CUDA(p, launch_rect_mask(p->d_map.as<float2>(), g.orows, g.ocols, g.frows, g.fcols, p->d_tmp.as<uint8_t>(), p->stream, &launches));
+    p->kernel_launches += launches;
+    RIP_CUDA(p, cudaMemcpyAsync(out, p->d_tmp.ptr, bytes, cudaMemcpyDeviceToHost, p->stream));
+    RIP_CUDA(p, cudaStreamSynchronize(p->stream));
+    return RIP_OK;
+  }
   const uint8_t* src = nullptr;
   int r = 0, c = 0;
   if (which == RIP_IMAGE_PROCESSED) { src = p->d_out.as<uint8_t>(); r = g.orows; c = g.ocols; }
@@ -831,8 +880,12 @@ int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame
   const size_t pitch = (size_t)cols * channels;
   if (in_frame_stride < pitch * rows) return p->fail(RIP_ERR_INVALID_ARGUMENT, "in_frame_stride smaller than a frame");
   if (out_frame_stride < (size_t)g.orows * g.ocols * g.ochannels) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
-  return process_device(p, p->scratch, g, d_in, pitch, in_frame_stride, n_frames, d_out, out_frame_stride, d_dist_color, 0, false,
-                        static_cast<cudaStream_t>(cuda_stream), /*keep_bgr_color=*/false);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  Scratch& sc = p->dev_scratch[st];
+  rc = process_device(p, sc, g, d_in, pitch, in_frame_stride, n_frames, d_out, out_frame_stride, d_dist_color, 0, false, st,
+                      /*keep_bgr_color=*/false);
+  if (rc == RIP_OK && p->hs.p.wb_enabled && p->hs.p.wb_method == "ccc") { p->ccc_pending_gains = &sc.gains; p->ccc_pending_stream = st; }
+  return rc;
 }
 
 int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames, int rows, int cols,
@@ -857,8 +910,9 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
   // consistency on, all chunks go through one slot so that they execute in order on one CUDA stream.
   const Params& q = p->hs.p;
   const int n_slots = (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency) ? 1 : kSlots;
-  int slot_i = 0;
+  int slot_i = 0, last_slot = -1;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, slot_i = (slot_i + 1) % n_slots) {
+    last_slot = slot_i;
     const int n = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
     Slot& s = p->slots[slot_i];
     RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again
@@ -873,6 +927,11 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
                                   cudaMemcpyDeviceToHost, s.stream));
   }
   for (Slot& s : p->slots) RIP_CUDA(p, cudaStreamSynchronize(s.stream));
+  if (last_slot >= 0 && q.wb_enabled && q.wb_method == "ccc") {  // the estimate of the batch's last frame, like after apply()
+    Slot& s = p->slots[last_slot];
+    if ((rc = ccc_fetch_last(p->ccc, s.scratch.gains, s.stream, p->last_error)) != RIP_OK) return rc;
+    p->ccc_pending_gains = nullptr;
+  }
   return RIP_OK;
 }
 

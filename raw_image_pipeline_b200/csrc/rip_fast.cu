@@ -615,11 +615,16 @@ cudaError_t launch_pca_stats_fast(const FrameParams& p, int sm_count, cudaStream
   if (!in_map_for(p, &im, TH_STATS)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * 8 * p.n_frames, stream);
   if (e != cudaSuccess) return e;
-  static int occ = 0;
+  static int occ_of_device[64] = {0};  // per device (benign race: every writer stores the same value)
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int occ = occ_of_device[dev & 63];
   if (occ == 0) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pca_stats_fast, NT, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
+    occ_of_device[dev & 63] = occ;
   }
   const long long tiles = total_tiles(p, TH_STATS), cap = (long long)sm_count * occ;
   const int grid = (int)(tiles < cap ? tiles : cap);

@@ -556,6 +556,29 @@ cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream
   return cudaGetLastError();
 }
 
+// Validity mask of the rectified image (the `rect_mask_` the reference declares but never fills, undistortion.hpp:136):
+// 255 where all four bilinear taps of cv::remap lie inside the source image -- the pixel is an interpolation of real
+// pixels only --, 0 where the constant border contributes.  Depends on the map and the source size only.
+__global__ void __launch_bounds__(256) k_rect_mask(const float2* __restrict__ map, int orows, int ocols, int rows, int cols,
+                                                   uint8_t* __restrict__ mask) {
+  const long long total = (long long)orows * ocols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float2 m = __ldg(map + i);
+    const int ix = remap_fix(m.x) >> 5, iy = remap_fix(m.y) >> 5;  // the integers cv::remap derives (frame_math.cuh remap_pixel)
+    mask[i] = (ix >= 0 && ix + 1 < cols && iy >= 0 && iy + 1 < rows) ? 255 : 0;
+  }
+}
+
+cudaError_t launch_rect_mask(const float2* map, int orows, int ocols, int rows, int cols, uint8_t* mask, cudaStream_t stream, int* launches) {
+  const long long total = (long long)orows * ocols;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (launches) ++*launches;
+  k_rect_mask<<<(int)blocks, 256, 0, stream>>>(map, orows, ocols, rows, cols, mask);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_remap_bgrx(const RemapParams& p, int sm_count, cudaStream_t stream, int* launches) {
   (void)sm_count;
   if (p.ocols <= 0 || p.orows <= 0 || p.n_frames <= 0) return cudaSuccess;

@@ -1,26 +1,32 @@
 // Fused chain, strip kernel: the fast path's debayer -> flip -> WB -> colour calibration -> gamma -> vignetting -> enhancer
-// (raw_image_pipeline.hpp:143-166) for camera-shaped Bayer frames, organised so that no warp ever waits for another:
+// (raw_image_pipeline.hpp:143-166) for camera-shaped Bayer frames, organised so that no warp ever waits for another and
+// the per-row code is one straight line:
 //
-//   * a WARP owns a vertical strip of the frame, 128 pixels wide (32 lanes x 4 adjacent pixels) and `seg_h` rows tall,
-//     and walks down its rows.  Every Bayer row is read from shared memory exactly once (three 32-bit words per lane)
-//     into a sliding three-row window held in registers (bayer_window.cuh), so the demosaic costs ~9 instructions per
-//     pixel instead of the ~25 of a per-row 3x3 fetch;
+//   * a WARP owns a vertical strip of the frame, 128 pixels wide (32 lanes x 4 adjacent pixels) and up to `seg_h` rows
+//     tall, and walks down its rows.  Every Bayer row is read from shared memory exactly once (three 32-bit words per
+//     lane) into a sliding three-row window held in registers (bayer_window.cuh);
 //   * each warp feeds itself: lane 0 has the TMA unit copy chunks of 4 rows x 160 bytes (strip + 16-byte halo columns,
 //     zero fill outside the frame) into the warp's private ring of three chunks, two chunks ahead of the arithmetic,
-//     completion signalled on the warp's own mbarriers.  There is no __syncthreads() in the steady state (only when the
-//     CTA moves on to another frame and swaps the per-frame white-balance table);
+//     completion signalled on the warp's own mbarriers.  A chunk is exactly four output rows: the loop body is the
+//     unrolled code of 4 (light stage sets) or 2 x 2 (heavy ones, to stay inside the instruction cache) rows, with the
+//     CFA-phase selectors of even and odd rows hoisted out of it.  There is no __syncthreads() in the steady state (only
+//     when the CTA moves on to another frame and swaps the per-frame white-balance table);
+//   * OpenCV's border rule (output row 0 = the interior formula at row 1, row H-1 = at row H-2) is served by two extra
+//     one-row units per strip and frame instead of special cases in the row loop;
 //   * the 4-byte intermediate (B,G,R,0 -- what the undistortion gather reads) leaves the registers directly: one
 //     16-byte store per lane and row, 512 contiguous bytes per warp.  BGR8 output (12 bytes per lane) is assembled in a
-//     per-warp staging buffer and written by the warp's own TMA stores, two rows at a time;
+//     per-warp staging buffer and written by the warp's own TMA stores, four rows at a time;
 //   * a CTA is 8 warps = 8 adjacent strips; CTA units (frame, row segment, strip group) are dealt round-robin over a
 //     persistent grid, so the grid works on a narrow band of one or two frames at a time (L2 locality of the vignetting
 //     mask and of the per-frame tables).
 //
-// Per-pixel arithmetic: pixel_math.cuh (bit-exact against the cv2 oracle, tests/test_pixel_math_host.py).
+// Per-pixel arithmetic: chain_quad.cuh (bit-exact against pixel_math.cuh, which is bit-exact against the cv2 oracle).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "bayer_window.cuh"
 #include "chain_quad.cuh"
@@ -34,25 +40,32 @@ namespace {
 
 constexpr int SW = 128;             // strip width in pixels
 constexpr int NW = 8, NT = NW * 32;  // warps (= adjacent strips) per CTA
-constexpr int CH = 4;               // Bayer rows per TMA chunk
+constexpr int CH = 4;               // Bayer rows per TMA chunk = output rows per pass of the loop body
 constexpr int NS = 3;               // chunks in a warp's ring
 constexpr int ROW_B = 160, ROW_W = ROW_B / 4;  // staged Bayer row: columns x0-16 .. x0+143 (the TMA needs 16-byte aligned x)
 constexpr int X_WORD0 = 3;          // word holding columns x0-4 .. x0-1
 constexpr int CHUNK_B = ROW_B * CH;
-constexpr int OR_ROWS = 2;          // rows per output TMA store (BGR8 only)
-constexpr int OUT_ROW_B = SW * 3;
+constexpr int OUT_ROW_B = SW * 3;   // BGR8 staging row
+constexpr int GROUP_B = CH * OUT_ROW_B;
 
+// Shared memory of a CTA (dynamic): [padding][tables][warp rings][BGR8 staging][mbarriers].  chain_quad.cuh merges table
+// indices into table addresses with OR / byte permutes, which needs the table block on a 4096-byte boundary of the SHARED
+// WINDOW ADDRESS; static __shared__ alignment cannot give that (the window starts with 1 KB of system-reserved memory,
+// alignas() counts from the end of it), so the block is aligned at run time and the launch requests 4 KB of slack.
 template <uint32_t STAGES, bool BGRX>
 struct StripSmem {
   // tables: a verbatim copy of the strip blob (chain_tables.hpp SOFF_*), truncated to what the stage set reads
-  static constexpr int TBL = (STAGES & ST_ENH) ? STRIP_TABLE_BYTES : (STAGES & ST_VIG) ? SOFF_SV : (STAGES & ST_GAMMA) ? SOFF_G2 : (STAGES & ST_WB) ? SOFF_GAMMA : 16;
+  static constexpr int TBL_RAW = (STAGES & ST_ENH) ? STRIP_TABLE_BYTES : (STAGES & ST_VIG) ? SOFF_SV : (STAGES & ST_GAMMA) ? SOFF_G2 : (STAGES & ST_WB) ? SOFF_GAMMA : 128;
+  static constexpr int TBL = (TBL_RAW + 127) / 128 * 128;
   static constexpr int COPY_LO = (STAGES & ST_VIG) ? 0 : SOFF_GAMMA;  // first blob byte a stage set without vignetting needs
-  static constexpr int OUTB = BGRX ? 128 : NW * 2 * OR_ROWS * OUT_ROW_B;
-  alignas(4096) uint8_t tables[(TBL + 127) / 128 * 128];
-  alignas(128) uint8_t in[NW][NS][CHUNK_B];
-  alignas(128) uint8_t out[OUTB];  // [warp][buffer][row][384]
-  alignas(8) unsigned long long mbar[NW][NS];
+  static constexpr int OFF_IN = TBL;                                   // [warp][slot][CHUNK_B]
+  static constexpr int OFF_OUT = OFF_IN + NW * NS * CHUNK_B;           // [warp][buffer][row][384]
+  static constexpr int OFF_MBAR = OFF_OUT + (BGRX ? 0 : NW * 2 * GROUP_B);
+  static constexpr int BYTES = OFF_MBAR + NW * NS * 8;
+  static constexpr int REQUEST = BYTES + 4096 - 16;  // dynamic shared memory is 16-byte aligned: at most 4080 bytes of padding
 };
+
+extern __shared__ uint8_t strip_smem_raw[];
 
 // the enhancer's row-tail pixels (cv2's scalar loop rounds where the vector loop truncates, pixel_math.cuh): rare
 // (only frames whose width is not a multiple of 32), so out of line and compiled once; the pixel sits in byte 0.
@@ -67,33 +80,35 @@ __device__ __noinline__ uint32_t chain_px_tail(uint32_t Bw, uint32_t Gw, uint32_
 constexpr uint32_t KEY_WBG = 32u;
 template <uint32_t KEY, bool BGRX, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant__ FrameParams P, const __grid_constant__ StripGeom G,
-                                                    const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                                                    const __grid_constant__ CUtensorMap out_map1) {
+                                                       const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                                                       const __grid_constant__ CUtensorMap out_map1) {
   constexpr uint32_t STAGES = KEY & ST_ALL;
   constexpr bool WBG = (KEY & KEY_WBG) != 0;
-  __shared__ StripSmem<STAGES, BGRX> sm;
+  constexpr int UNR = (STAGES & (ST_VIG | ST_ENH)) ? 2 : 4;  // rows of straight-line code (the chain of 4 x 4 pixels would not fit the I-cache)
+  using L = StripSmem<STAGES, BGRX>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned long long* mbar = sm.mbar[warp];
+  uint8_t* const sm = strip_smem_raw + ((0u - smem_u32(strip_smem_raw)) & 4095u);  // 4096-byte aligned shared-window address
+  uint8_t* const sm_in = sm + L::OFF_IN + warp * (NS * CHUNK_B);   // this warp's ring
+  uint8_t* const sm_out = sm + L::OFF_OUT + warp * (2 * GROUP_B);  // this warp's two staging groups (BGR8 only)
+  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(sm + L::OFF_MBAR) + warp * NS;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
     fence_mbar_init();
   }
   if (STAGES & (ST_GAMMA | ST_VIG | ST_ENH)) {
-    constexpr int LO = StripSmem<STAGES, BGRX>::COPY_LO / 16, HI = StripSmem<STAGES, BGRX>::TBL / 16;
+    constexpr int LO = L::COPY_LO / 16, HI = L::TBL_RAW / 16;
     const uint4* src = reinterpret_cast<const uint4*>(P.strip_tables);
-    uint4* dst = reinterpret_cast<uint4*>(sm.tables);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
     for (int i = LO + tid; i < HI; i += NT) dst[i] = __ldg(src + i);
   }
-  // chain_quad.cuh merges indices into table addresses with OR / byte permutes: needs this alignment of the shared address
-  if ((smem_u32(sm.tables) & 4095u) != 0u) __trap();
   __syncthreads();
-  const StripTables T = strip_tables_at(smem_u32(sm.tables));
+  const StripTables T = strip_tables_at(taddr_of_shared(sm));
   const bool rev = P.angle == 180;
   const int tail_start = P.ocols & ~31;
   int cur_frame = -1;
-  uint32_t slot = 0, ph = 0;  // this warp's ring: next slot to consume, per-slot mbarrier parities
-  uint32_t obuf = 0;          // BGR8 staging: buffer being filled
+  uint32_t slot = 0, ph = 0;  // this warp's ring: slot of the next chunk to consume, per-slot mbarrier parities
+  uint32_t obuf = 0;          // BGR8 staging: group being filled
 
   for (long long u = blockIdx.x; u < G.total_units; u += gridDim.x) {
     const int frame = (int)(u / G.units_per_frame);
@@ -102,132 +117,144 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
     if ((STAGES & ST_WB) && frame != cur_frame) {  // uniform over the CTA
       __syncthreads();                             // nobody reads the previous frame's table any more
       const float* src = P.wbf + (size_t)frame * 768;
-      for (int i = tid; i < 768; i += NT) sm.tables[SOFF_WB + i] = (uint8_t)__float2int_rz(src[i]);  // plain load: written by a prior kernel
+      for (int i = tid; i < 768; i += NT) sm[SOFF_WB + i] = (uint8_t)__float2int_rz(src[i]);  // plain load: written by a prior kernel
       __syncthreads();
       cur_frame = frame;
     }
     const int strip = grp * NW + warp;
     if (strip >= G.nstrips) continue;
 
-    // strips and segments are anchored in the OUTPUT frame (TMA stores reject negative coordinates, loads zero-fill)
-    const int oya = seg * G.seg_h, oyb = min(oya + G.seg_h, P.orows);
+    // Rows of the unit: `n` centre rows ca .. ca + n - 1 (the rows the demosaic formula is evaluated at), emitted as the
+    // input-frame rows ye0 .. ye0 + n - 1.  Segments cover the interior rows 1 .. H-2; the two border units re-evaluate
+    // rows 1 and H-2 for the frame's first and last row (OpenCV's border rule, frame_math.cuh demosaic_at).
+    int ca, n, ye0;
+    if (seg < G.nseg) { ca = 1 + seg * G.seg_h; n = min(G.seg_h, P.rows - 1 - ca); ye0 = ca; }
+    else if (seg == G.nseg) { ca = 1; n = 1; ye0 = 0; }
+    else { ca = P.rows - 2; n = 1; ye0 = P.rows - 1; }
+
+    // strips are anchored in the OUTPUT frame (TMA stores reject negative coordinates, loads zero-fill)
     const int ox0 = strip * SW;
     const int x0 = rev ? P.cols - SW - ox0 : ox0;  // may be negative for the last strip of a rotated frame
-    const int iya = rev ? P.rows - oyb : oya, iyb = rev ? P.rows - oya : oyb;  // input rows [iya, iyb)
     const int x = x0 + 4 * lane;
     const bool active = x >= 0 && x < P.cols;
-    // OpenCV's border rule: output row y is the interior formula at row clamp(y, 1, H-2) (frame_math.cuh demosaic_at)
-    const int c_first = min(max(iya, 1), P.rows - 2), c_last = min(max(iyb - 1, 1), P.rows - 2);
-    const int r0 = c_first - 1;               // first Bayer row this unit reads
-    const int nrows = c_last + 2 - r0;        // rows r0 .. c_last + 1
-    const int nchunks = (nrows + CH - 1) / CH;
-    int issued = nchunks < NS ? nchunks : NS;
+    const int xc = min(max(x, 0), P.cols - 4);     // inactive lanes compute on a valid address and store nothing
+    const int oxb = rev ? P.cols - 4 - x : x;      // output column of the quad's lowest-address pixel
+    const bool tail_quad = (STAGES & ST_ENH) && oxb >= tail_start;
+    const uint32_t colfix = x == 0 ? 0x3211u : (x + 4 == P.cols ? 0x2210u : 0x3210u);  // column 0 <- 1, W-1 <- W-2
+    const BayerPhase phase = bayer_phase(ca, P.cfa);  // "even" rows: ca, ca + 2, ...
+
+    // chunk k of the unit holds Bayer rows ca - 3 + 4k .. ca + 4k: chunk 0 only supplies the two rows above the first
+    // centre's bottom row, chunk k >= 1 the bottom rows of centres ca + 4(k-1) .. ca + 4(k-1) + 3
+    const int nq = (n + CH - 1) / CH;
+    int issued = nq + 1 < NS ? nq + 1 : NS;
     if (lane == 0) {
       uint32_t s = slot;
       for (int c = 0; c < issued; ++c) {
         mbar_expect_tx(&mbar[s], CHUNK_B);
-        tma_load_3d(sm.in[warp][s], &in_map, &mbar[s], x0 - 16, r0 + c * CH, frame);
+        tma_load_3d(sm_in + s * CHUNK_B, &in_map, &mbar[s], x0 - 16, ca - 3 + c * CH, frame);
         s = s + 1 == NS ? 0 : s + 1;
       }
     }
-    // The first chunk (rows r0 .. r0 + 3) holds the first two rows of the window.
+    auto refill_and_advance = [&]() {  // the chunk in `slot` is consumed: load the unit's next unissued chunk into it
+      __syncwarp();
+      if (issued <= nq) {
+        if (lane == 0) {
+          mbar_expect_tx(&mbar[slot], CHUNK_B);
+          tma_load_3d(sm_in + slot * CHUNK_B, &in_map, &mbar[slot], x0 - 16, ca - 3 + issued * CH, frame);
+        }
+        ++issued;
+      }
+      slot = slot + 1 == NS ? 0 : slot + 1;
+    };
     mbar_wait(&mbar[slot], (ph >> slot) & 1u);
     ph ^= 1u << slot;
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(sm.in[warp][slot]) + X_WORD0 + lane;
-    BayerRow rn = load_bayer_row(rowp, r0, P.cfa);
-    BayerRow rm = load_bayer_row(rowp + ROW_W, r0 + 1, P.cfa);
-    const uint32_t colfix = x == 0 ? 0x3211u : (x + 4 == P.cols ? 0x2210u : 0x3210u);  // column 0 <- 1, W-1 <- W-2
-    const int oxb = rev ? P.cols - 4 - x : x;  // output column of the quad's lowest-address pixel
-    const bool tail_quad = (STAGES & ST_ENH) && oxb >= tail_start;
-    uint8_t* const outf = P.out + (long long)frame * P.out_frame_stride;
-    const float* vig = (STAGES & ST_VIG) ? P.vig + (size_t)iya * P.vig_pitch + x : nullptr;
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(sm_in + slot * CHUNK_B) + X_WORD0 + lane;
+    BayerRow rn = load_bayer_row<true>(rowp + 2 * ROW_W, phase);   // row ca - 1
+    BayerRow rm = load_bayer_row<false>(rowp + 3 * ROW_W, phase);  // row ca
+    refill_and_advance();
 
-    for (int j = 2; j < nrows; ++j) {  // j: index, counted from r0, of the window's bottom row; centre row c = r0 + j - 1
-      if ((j & (CH - 1)) == 0) {       // the bottom row enters the next chunk: the previous one is consumed, refill its slot
+    const int oy0 = rev ? P.rows - 1 - ye0 : ye0;  // output row of the first emitted row; the following ones go down (up when rotated)
+    // per-lane positions as 32-bit offsets from uniform bases (a frame of the 4-byte intermediate is < 2^31 bytes)
+    uint8_t* const outf = P.out + (long long)frame * P.out_frame_stride;
+    const int ostep = rev ? -P.out_pitch : P.out_pitch;
+    int ooff = oy0 * P.out_pitch + oxb * 4;       // BGRX only
+    int voff = ye0 * P.vig_pitch + xc;            // mask in input-frame coordinates, floats
+    const int lane_pos = 12 * (rev ? 31 - lane : lane);
+    int done = 0;
+
+    for (int k = 1; k <= nq; ++k) {
+      mbar_wait(&mbar[slot], (ph >> slot) & 1u);
+      ph ^= 1u << slot;
+      rowp = reinterpret_cast<const uint32_t*>(sm_in + slot * CHUNK_B) + X_WORD0 + lane;
+      const int nv = min(CH, n - done);  // rows of this chunk that exist (4 except at the end of a ragged unit)
+      uint8_t* sp = nullptr;             // BGR8: this lane's place in the staging row being filled
+      if (!BGRX) {
+        if (lane == 0) tma_wait_read<1>();  // the group about to be filled was handed to the TMA two groups ago
         __syncwarp();
-        if (issued < nchunks) {
-          if (lane == 0) {
-            mbar_expect_tx(&mbar[slot], CHUNK_B);
-            tma_load_3d(sm.in[warp][slot], &in_map, &mbar[slot], x0 - 16, r0 + issued * CH, frame);
-          }
-          ++issued;
-        }
-        slot = slot + 1 == NS ? 0 : slot + 1;
-        mbar_wait(&mbar[slot], (ph >> slot) & 1u);
-        ph ^= 1u << slot;
-        rowp = reinterpret_cast<const uint32_t*>(sm.in[warp][slot]) + X_WORD0 + lane;
+        sp = sm_out + obuf * GROUP_B + (rev ? (CH - 1) * OUT_ROW_B : 0) + lane_pos;
       }
-      const int c = r0 + j - 1;
-      const BayerRow rs = load_bayer_row(rowp + (j & (CH - 1)) * ROW_W, c + 1, P.cfa);
-      uint32_t Bw, Gw, Rw;
-      demosaic_window(rn, rm, rs, c, P.cfa, Bw, Gw, Rw);
-      if (colfix != 0x3210u) { Bw = prmt(Bw, 0u, colfix); Gw = prmt(Gw, 0u, colfix); Rw = prmt(Rw, 0u, colfix); }
-      rn = rm; rm = rs;
-      // OpenCV's border rule: centre row 1 also serves output row 0, centre row H-2 also row H-1
-      const int ylo = c == 1 ? iya : c, yhi = c == P.rows - 2 ? iyb - 1 : c;
-      for (int y = ylo; y <= yhi; ++y) {
-        const int oy = rev ? P.rows - 1 - y : y;
-        uint32_t px[4] = {0u, 0u, 0u, 0u};
-        if (active) {
-          float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-          if (STAGES & ST_VIG) {  // mask stored in input-frame coordinates
-            const float4 v = __ldg(reinterpret_cast<const float4*>(vig));
-            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
-          }
-          if (!tail_quad) {
-            chain_quad<STAGES, WBG, false>(Bw, Gw, Rw, m, P.k, T, px);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) px[k] = chain_px_tail<STAGES>(Bw >> (8 * k), Gw >> (8 * k), Rw >> (8 * k), m[k], P.k, T);
-          }
+      // one output row: row `tt` = h * UNR + t of the chunk (t is a compile-time constant: the row's parity is t's)
+      auto row_step = [&](auto tc, int h) {
+        constexpr int t = decltype(tc)::value;
+        const int tt = h * UNR + t;  // row of the chunk: centre row ca + 4(k-1) + tt, whose parity is t's
+        const BayerRow rs = load_bayer_row<(t & 1) == 0>(rowp + tt * ROW_W, phase);  // the bottom row has the other parity
+        uint32_t Bw, Gw, Rw;
+        demosaic_window<(t & 1) != 0>(rn, rm, rs, phase, Bw, Gw, Rw);
+        rn = rm; rm = rs;
+        if (colfix != 0x3210u) { Bw = prmt(Bw, 0u, colfix); Gw = prmt(Gw, 0u, colfix); Rw = prmt(Rw, 0u, colfix); }
+        float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (STAGES & ST_VIG) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + voff));
+          m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+          voff += P.vig_pitch;
         }
-        if (STAGES & ST_VIG) vig += P.vig_pitch;
-        if (BGRX) {
-          if (active) {
-            const uint4 v = rev ? make_uint4(px[3], px[2], px[1], px[0]) : make_uint4(px[0], px[1], px[2], px[3]);
-            *reinterpret_cast<uint4*>(outf + (size_t)oy * P.out_pitch + (size_t)oxb * 4) = v;
-          }
+        uint32_t px[4];
+        if (!tail_quad) {
+          chain_quad<STAGES, WBG, false>(Bw, Gw, Rw, m, P.k, T, px);
         } else {
-          const int jo = (y - iya) & (OR_ROWS - 1);
-          if (jo == 0) {  // the buffer about to be filled was handed to the TMA two groups ago
-            if (lane == 0) tma_wait_read<1>();
-            __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) px[j] = chain_px_tail<STAGES>(Bw >> (8 * j), Gw >> (8 * j), Rw >> (8 * j), m[j], P.k, T);
+        }
+        if (BGRX) {
+          if (active && tt < nv) {
+            if (rev) *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[3], px[2], px[1], px[0]);
+            else *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[0], px[1], px[2], px[3]);
           }
-          uint8_t* grp_base = sm.out + (size_t)((warp * 2 + obuf) * OR_ROWS) * OUT_ROW_B;
-          if (active) {
-            uint32_t* o = reinterpret_cast<uint32_t*>(grp_base + (rev ? OR_ROWS - 1 - jo : jo) * OUT_ROW_B + 12 * (rev ? 31 - lane : lane));
-            if (!rev) { o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542); }
-            else { o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542); }
-          }
-          if (jo == OR_ROWS - 1) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {  // 4-byte elements; the TMA unit clips columns beyond the frame
-              tma_store_3d(&out_map, grp_base, ox0 * 3 / 4, rev ? oy : oy - (OR_ROWS - 1), frame);
-              tma_commit();
-            }
-            obuf ^= 1u;
-          }
+          ooff += ostep;
+        } else {  // lanes beyond the frame edge write staging bytes the TMA store clips
+          uint32_t* o = reinterpret_cast<uint32_t*>(sp);
+          if (rev) { o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542); sp -= OUT_ROW_B; }
+          else { o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542); sp += OUT_ROW_B; }
+        }
+      };
+#pragma unroll 1
+      for (int h = 0; h < CH / UNR; ++h) {
+        row_step(std::integral_constant<int, 0>{}, h);
+        row_step(std::integral_constant<int, 1>{}, h);
+        if constexpr (UNR == 4) {
+          row_step(std::integral_constant<int, 2>{}, h);
+          row_step(std::integral_constant<int, 3>{}, h);
         }
       }
-    }
-    if (!BGRX) {  // rows left over when the unit's height is not a multiple of OR_ROWS: one-row stores
-      const int left = (iyb - iya) & (OR_ROWS - 1);
-      if (left) {
-        uint8_t* grp_base = sm.out + (size_t)((warp * 2 + obuf) * OR_ROWS) * OUT_ROW_B;
+      if (!BGRX) {  // hand the group to the TMA: one 4-row store, or row by row at the end of a ragged unit
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          for (int jo = 0; jo < left; ++jo) {
-            const int y = iyb - left + jo, oy = rev ? P.rows - 1 - y : y;
-            tma_store_3d(&out_map1, grp_base + (rev ? OR_ROWS - 1 - jo : jo) * OUT_ROW_B, ox0 * 3 / 4, oy, frame);
+          const uint8_t* gb = sm_out + obuf * GROUP_B;
+          const int oyg = oy0 + (rev ? -done : done);  // output row of the group's first processed row
+          if (nv == CH) {
+            tma_store_3d(&out_map, gb, ox0 * 3 / 4, rev ? oyg - (CH - 1) : oyg, frame);  // 4-byte elements; clipped at the frame edge
+          } else {
+            for (int j = 0; j < nv; ++j)
+              tma_store_3d(&out_map1, gb + (rev ? CH - 1 - j : j) * OUT_ROW_B, ox0 * 3 / 4, rev ? oyg - j : oyg + j, frame);
           }
           tma_commit();
         }
         obuf ^= 1u;
       }
+      done += CH;
+      refill_and_advance();
     }
-    slot = slot + 1 == NS ? 0 : slot + 1;  // the unit's last chunk is consumed
   }
   if (!BGRX && lane == 0) tma_wait_read<0>();  // shared memory must stay valid until the last store has read it
 }
@@ -235,21 +262,23 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
 template <uint32_t KEY, bool BGRX, int MINB>
 cudaError_t launch_strip_instance(const FrameParams& p, const StripGeom& g, const CUtensorMap& im, const CUtensorMap& om, const CUtensorMap& om1,
                                   int sm_count, cudaStream_t stream) {
-  static_assert(sizeof(StripSmem<(KEY & ST_ALL), BGRX>) <= 48 * 1024, "k_fused_strip keeps its shared memory static");
+  constexpr int smem = StripSmem<(KEY & ST_ALL), BGRX>::REQUEST;
   static int occ_of_device[64] = {0};  // per instantiation and device (benign race: every writer stores the same value)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   int occ = occ_of_device[dev & 63];
   if (occ == 0) {
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_strip<KEY, BGRX, MINB>, NT, 0);
+    e = cudaFuncSetAttribute(k_fused_strip<KEY, BGRX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_strip<KEY, BGRX, MINB>, NT, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     occ_of_device[dev & 63] = occ;
   }
   const long long cap = (long long)sm_count * occ;
   const int grid = (int)(g.total_units < cap ? g.total_units : cap);
-  k_fused_strip<KEY, BGRX, MINB><<<grid, NT, 0, stream>>>(p, g, im, om, om1);
+  k_fused_strip<KEY, BGRX, MINB><<<grid, NT, smem, stream>>>(p, g, im, om, om1);
   return cudaGetLastError();
 }
 

@@ -145,6 +145,10 @@ class RawImagePipeline:
         orows, ocols, och = self.output_shape(frames.shape[1:], encoding)
         if out is None:
             out = np.empty((n, orows, ocols, och), np.uint8)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags.c_contiguous or not out.flags.writeable
+              or out.size != n * orows * ocols * och):
+            # the C entry point writes n tightly packed frames through the raw pointer: anything else corrupts memory
+            raise ValueError(f"out must be a writable C-contiguous uint8 array of {n}x{orows}x{ocols}x{och} values")
         self.process_batch_ptr(frames.ctypes.data, n, rows, cols, ch, encoding, out.ctypes.data, host=True)
         return out
 
@@ -155,6 +159,8 @@ class RawImagePipeline:
         orows, ocols, och = self.output_shape((rows, cols, channels), encoding)
         ins = in_frame_stride if in_frame_stride is not None else rows * cols * channels
         outs = out_frame_stride if out_frame_stride is not None else orows * ocols * och
+        if n <= 0 or ins < rows * cols * channels or outs < orows * ocols * och:
+            raise ValueError("process_batch_ptr: n must be positive and the frame strides at least one frame")
         if host:
             self._check(self._lib.rip_apply_batch_host(self._h, in_ptr, ins, n, rows, cols, channels, encoding.encode(),
                                                        out_ptr, outs))
@@ -252,6 +258,10 @@ class RawImagePipeline:
 
     # ---- inspection --------------------------------------------------------------------------
     def kernel_launches(self) -> int: return self._get_int("stats/kernel_launches")
+    def ccc_uv(self) -> Tuple[int, int]:
+        """(u, v) = arg-max of the CCC response for the last frame processed (single frame or last of a batch)."""
+        return self._get_int("stats/ccc_u"), self._get_int("stats/ccc_v")
+    def ccc_gains(self) -> np.ndarray: return self._get_doubles("stats/ccc_gains")
     def log(self) -> str: return self._get_string("log")
 
     def debug_table(self, name: str, rows: int = 0, cols: int = 0) -> bytes:
