@@ -2,15 +2,22 @@
 """Benchmark of the RAW hot path (BASELINE.json metric: Mpix/s end-to-end at 12 MP full chain;
 fused-kernel HBM GB/s vs peak).
 
-    python bench.py --gpus 1 --steps 5 --warmup 3            # this framework (B200 kernels)
+    python bench.py --gpus 1 --steps 5 --warmup 3            # this framework (B200 kernels), BASELINE configs[2]
+    python bench.py --config 2 | 4 | 5                        # the other BASELINE configurations
     python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference's CPU path (cv2 oracle)
     torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, frames sharded (weak scaling)
 
-A "step" is one pass of the hot path over one batch of synthetic Bayer frames: BASELINE.json
-configs[2] = 64 x 4032x3040 bayer_rggb8, full chain (flip 180, pca WB, colour calibration, gamma,
-vignetting, enhancer, undistortion).  `value` = device-resident throughput, `e2e` = the same
-through the host-buffer C-ABI entry point with H2D/D2H copies inside the timed region.
-Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path over one batch of synthetic Bayer frames.  Default: BASELINE.json configs[2] =
+64 x 4032x3040 bayer_rggb8, full chain (flip 180, pca WB, colour calibration, gamma, vignetting, enhancer, undistortion).
+`value` = DEVICE-RESIDENT throughput (inputs and outputs in HBM, CUDA events), `e2e` = the same through the host-buffer
+C-ABI entry point with H2D/D2H copies inside the timed region (the end-to-end number).  Prints ONE JSON line on rank 0.
+
+  --config 2   1 x 1920x1080 bayer_bggr8, full chain: latency-bound -- a step = `--frames` single-frame calls;
+               `value` = device-resident one-frame launches, `e2e` = RawImagePipeline::apply() from/to pageable numpy
+               arrays; `latency_us` reports p50/p99 per frame with and without the CUDA-graph replay.
+  --config 4   one 1080p camera stream per GPU (rank), >= 256 frames each, frame by frame host to host;
+               `streams` reports per-stream p50/p99 latency and Mpix/s, `value`/`e2e` the aggregate.
+  --config 5   64 x 3840x2160 per GPU, full chain with CCC white balance + undistortion, distribution N.
 """
 from __future__ import annotations
 
@@ -27,13 +34,22 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-ROWS, COLS, ENC = 3040, 4032, "bayer_rggb8"
 CC = [2.4276948, 0.21479778, -0.30818, 0.09277014, 1.1962607, -0.09772757, -0.24436986, -0.22239459, 2.099912]
 CALIB_D = [-0.0396482888762527, -0.00367688950406141, 0.00391742438164282, -0.00178738156007817]
 METRIC = "Mpix/s end-to-end at 12MP full chain"
-WORKLOAD = ("BASELINE configs[2]: batch of 4032x3040 bayer_rggb8 frames, full chain = debayer + flip 180 + pca white "
-            "balance + colour calibration (example matrix) + gamma 0.8 + vignetting (1.5,1e-3,1e-6) + HSV enhancer "
-            "(sat 1.2) + fisheye undistortion (balance 0, fov 0.8)")
+CHAIN = ("debayer + flip 180 + {wb} white balance + colour calibration (example matrix) + gamma 0.8 + vignetting "
+         "(1.5,1e-3,1e-6) + HSV enhancer (sat 1.2) + fisheye undistortion (balance 0, fov 0.8)")
+CONFIGS = {
+    2: dict(rows=1080, cols=1920, enc="bayer_bggr8", wb="pca", frames=64, mode="latency",
+            workload="BASELINE configs[1]: 1920x1080 bayer_bggr8 frames one at a time, full chain = " + CHAIN.format(wb="pca")),
+    3: dict(rows=3040, cols=4032, enc="bayer_rggb8", wb="pca", frames=64, mode="batch",
+            workload="BASELINE configs[2]: batch of 4032x3040 bayer_rggb8 frames, full chain = " + CHAIN.format(wb="pca")),
+    4: dict(rows=1080, cols=1920, enc="bayer_bggr8", wb="pca", frames=256, mode="latency",
+            workload="BASELINE configs[3]: one 1920x1080 bayer_bggr8 camera stream per GPU, frame by frame, full chain = " + CHAIN.format(wb="pca")),
+    5: dict(rows=2160, cols=3840, enc="bayer_rggb8", wb="ccc", frames=64, mode="batch",
+            workload="BASELINE configs[4]: batch of 3840x2160 bayer_rggb8 frames per GPU, full chain = " + CHAIN.format(wb="ccc (bright 0.8, dark 0.2, no temporal consistency)")),
+}
+ROWS, COLS, ENC = 3040, 4032, "bayer_rggb8"  # config 3 (module-level names kept for tools/)
 
 
 def calib_K(rows, cols):
@@ -41,12 +57,13 @@ def calib_K(rows, cols):
     return [347.548139773951 * sx, 0.0, 342.454373227748 * sx, 0.0, 347.434712422309 * sy, 271.368057185649 * sy, 0.0, 0.0, 1.0]
 
 
-def make_pipeline(rows, cols, device=None):
+def make_pipeline(rows, cols, device=None, wb="pca"):
     from raw_image_pipeline_b200 import RawImagePipeline
     cfg = os.path.join(ROOT, "raw_image_pipeline_b200", "config")
     p = RawImagePipeline(False, "", os.path.join(cfg, "alphasense_calib_example.yaml"), "", device=device)
     p.set_flip(True); p.set_flip_angle(180)
-    p.set_white_balance(True); p.set_white_balance_method("pca")
+    p.set_white_balance(True); p.set_white_balance_method(wb)
+    p.set_white_balance_saturation_threshold(0.8, 0.2); p.set_white_balance_temporal_consistency(False)
     p.set_color_calibration(True); p.set_color_calibration_matrix(CC)
     p.set_gamma_correction(True); p.set_gamma_correction_method("custom"); p.set_gamma_correction_k(0.8)
     p.set_vignetting_correction(True); p.set_vignetting_correction_parameters(1.5, 1e-3, 1e-6)
@@ -68,20 +85,22 @@ def make_witness_pipeline(device=None):
     return p
 
 
-def make_oracle(rows, cols):
-    """The reference's CPU path (call-for-call cv2 replay) -- used ONLY as the timed CPU baseline."""
+def make_oracle(rows, cols, wb="pca"):
+    """The reference's CPU path (call-for-call cv2 replay): the timed CPU baseline and the checker of the timed outputs."""
     from oracle import cv2_oracle as O
-    op = O.OracleParams(flip_enabled=True, flip_angle=180, wb_enabled=True, wb_method="pca", cc_enabled=True, cc_matrix=CC,
+    op = O.OracleParams(flip_enabled=True, flip_angle=180, wb_enabled=True, wb_method=wb, wb_bright_thr=0.8, wb_dark_thr=0.2,
+                        wb_temporal_consistency=False, cc_enabled=True, cc_matrix=CC,
                         gamma_enabled=True, gamma_k=0.8, vig_enabled=True, enh_enabled=True, enh_saturation_gain=1.2,
                         und_enabled=True, und_K=calib_K(rows, cols), und_D=CALIB_D, und_width=cols, und_height=rows,
                         und_balance=0.0, und_fov_scale=0.8)
-    return O.OraclePipeline(op)
+    return O.OraclePipeline(op, os.path.join(ROOT, "raw_image_pipeline_b200", "config", "ccc_model.bin") if wb == "ccc" else None)
 
 
-def make_frames(n, rows, cols, seed0, distinct=16):
+def make_frames(n, rows, cols, seed0, distinct=16, enc=ENC):
+    """n frames, of which min(n, 16) are distinct (generated on the host with Philox) and the rest repeats of them."""
     from raw_image_pipeline_b200 import synth
     d = min(n, distinct)
-    base = synth.bayer_batch(d, rows, cols, ENC, seed0, "N")
+    base = synth.bayer_batch(d, rows, cols, enc, seed0, "N")
     if d == n:
         return base
     return np.concatenate([base] * ((n + d - 1) // d))[:n]
@@ -172,44 +191,47 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def time_cpu_reference(rows, cols, n_sample, warm, threads=None):
+def time_cpu_reference(cfg, n_sample, warm, threads=None):
     import cv2
     if threads:
         cv2.setNumThreads(threads)
-    o = make_oracle(rows, cols)
-    frames = make_frames(n_sample, rows, cols, 3000)
+    rows, cols, enc = cfg["rows"], cfg["cols"], cfg["enc"]
+    o = make_oracle(rows, cols, cfg["wb"])
+    frames = make_frames(n_sample, rows, cols, 3000, enc=enc)
     for i in range(warm):
-        o.apply(frames[i % n_sample], ENC)
+        o.apply(frames[i % n_sample], enc)
     t0 = time.perf_counter()
     for i in range(n_sample):
-        o.apply(frames[i], ENC)
+        o.apply(frames[i], enc)
     dt = time.perf_counter() - t0
     return n_sample * rows * cols / dt / 1e6, cv2.getNumThreads(), dt
 
 
-def run_reference(args):
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import cv2
+    rows, cols, enc = cfg["rows"], cfg["cols"], cfg["enc"]
     n_sample = args.ref_frames
-    o = make_oracle(ROWS, COLS)
-    frames = make_frames(n_sample, ROWS, COLS, 3000)
+    o = make_oracle(rows, cols, cfg["wb"])
+    frames = make_frames(n_sample, rows, cols, 3000, enc=enc)
     for _ in range(args.warmup):
-        o.apply(frames[0], ENC)
+        o.apply(frames[0], enc)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for i in range(n_sample):
-            o.apply(frames[i], ENC)
+            o.apply(frames[i], enc)
     dt = time.perf_counter() - t0
-    value = args.steps * n_sample * ROWS * COLS / dt / 1e6
+    value = args.steps * n_sample * rows * cols / dt / 1e6
     cores = cv2.getNumThreads()
-    sample = f"{n_sample} frames of 4032x3040 per step (bounded sample of the 64-frame batch), cv2 {cv2.__version__}, {cores} threads"
+    sample = (f"{n_sample} frames of {cols}x{rows} per step (bounded sample of the workload's frames), cv2 {cv2.__version__}, "
+              f"{cores} threads; vignetting mask cached across frames (flatters the reference, SURVEY B-7)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": n_sample, "distribution": "N"},
+        "config": {"workload": cfg["workload"], "bench_config": args.config, "frames_per_step": n_sample, "distribution": "N"},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -217,34 +239,79 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+def copy_ceiling(world):
+    """Measured host<->device copy ceiling of the box at `world` GPUs (tools/pcie_probe, profiles/pcie_ceiling.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pcie_ceiling.json")) as f:
+            return json.load(f)["d2h_gbs_with_concurrent_h2d"].get(str(world))
+    except Exception:
+        return None
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+def percentiles(us):
+    a = np.sort(np.asarray(us, np.float64))
+    return {"p50": float(a[len(a) // 2]), "p99": float(a[min(len(a) - 1, int(len(a) * 0.99))]), "mean": float(a.mean()), "n": int(len(a))}
 
-    from raw_image_pipeline_b200 import sharding
 
-    def max_over_ranks(x):
-        return sharding.max_over_ranks(x, device=dev)
+class Job:
+    """rank / device / barrier plumbing shared by the modes"""
 
-    n, rows, cols = args.frames, ROWS, COLS
-    p = make_pipeline(rows, cols, device=local)
-    frames = make_frames(n, rows, cols, 3000 + 100 * rank)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        from raw_image_pipeline_b200 import sharding
+        return sharding.max_over_ranks(x, device=self.dev)
+
+    def gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def check_parity(p, cfg, frames, outputs, which):
+    """outputs[i] (numpy) against the oracle for the frame indices `which`"""
+    o = make_oracle(cfg["rows"], cfg["cols"], cfg["wb"])
+    nbad, maxd = 0, 0
+    for i in which:
+        ref, _ = o.apply(frames[i], cfg["enc"])
+        d = np.abs(outputs[i].astype(np.int16) - ref.astype(np.int16))
+        nbad += int(np.count_nonzero(d)); maxd = max(maxd, int(d.max()))
+    return {"frames_checked": len(which), "frames": list(which), "max_abs_diff": maxd, "differing_values": nbad,
+            "against": "oracle/cv2_oracle.py (cv2 replay of the reference CPU path), outputs of the timed call"}
+
+
+def run_batch(args, cfg):
+    """configs 3 and 5: one batch of frames per step and GPU"""
+    job = Job()
+    torch = job.torch
+    rank, world, local, dev = job.rank, job.world, job.local, job.dev
+    n, rows, cols, enc = args.frames, cfg["rows"], cfg["cols"], cfg["enc"]
+    p = make_pipeline(rows, cols, device=local, wb=cfg["wb"])
+    frames = make_frames(n, rows, cols, 3000 + 100 * rank, enc=enc)
     h_in = torch.from_numpy(frames).pin_memory()
     d_in = h_in.to(dev, non_blocking=True)
     d_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8, device=dev)
@@ -252,11 +319,11 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     def step_device():
-        p.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, ENC, d_out.data_ptr(), host=False, stream=stream)
+        p.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, enc, d_out.data_ptr(), host=False, stream=stream)
 
     for _ in range(args.warmup):
         step_device()
-    barrier()
+    job.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -267,8 +334,8 @@ def run_b200(args):
     for _ in range(args.steps):
         step_device()
     ev1.record()
-    barrier()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    job.barrier()
+    ms_total = job.max_over_ranks(ev0.elapsed_time(ev1))
     p._set_bool("profile/kernel_events", False)
     kernel_ms = p._get_doubles("stats/kernel_ms")
     launches = p.kernel_launches() - launches0
@@ -277,10 +344,10 @@ def run_b200(args):
 
     # ---- HBM-roofline witness: debayer + gamma only, same buffers -----------------------------------
     witness = None
-    if not args.no_witness:
+    if not args.no_witness and args.config == 3:
         pw = make_witness_pipeline(device=local)
         def step_w():
-            pw.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, ENC, d_out.data_ptr(), host=False, stream=stream)
+            pw.process_batch_ptr(d_in.data_ptr(), n, rows, cols, 1, enc, d_out.data_ptr(), host=False, stream=stream)
         for _ in range(3):
             step_w()
         torch.cuda.synchronize()
@@ -291,38 +358,43 @@ def run_b200(args):
         kw = pw._get_doubles("stats/kernel_ms")
         pw._set_bool("profile/kernel_events", False)
         w_ms = kw[2] / max(kw[4 + 2], 1.0)
-        witness = {"modules": "debayer + gamma (k=0.8)", "kernel": "k_fused<gamma, bayer>", "avg_launch_ms": w_ms,
+        witness = {"modules": "debayer + gamma (k=0.8)", "kernel": "k_fused_strip<gamma, BGR8>", "avg_launch_ms": w_ms,
                    "achieved_gbs": 4.0 * n * rows * cols / (w_ms * 1e-3) / 1e9 if w_ms > 0 else None,
                    "mpix_per_s": n * rows * cols / (w_ms * 1e-3) / 1e6 if w_ms > 0 else None}
         del pw
-        step_device()  # leave the full-chain result in d_out for the equality check below
-        torch.cuda.synchronize()
 
     # ---- end to end through the host-buffer entry point (pinned host memory, copies inside) ------
     h_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8).pin_memory()
 
     def step_host():
-        p.process_batch_ptr(h_in.data_ptr(), n, rows, cols, 1, ENC, h_out.data_ptr(), host=True)
+        p.process_batch_ptr(h_in.data_ptr(), n, rows, cols, 1, enc, h_out.data_ptr(), host=True)
 
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
-    e2e, dt_e2e, same = None, 0.0, None
+    e2e, dt_e2e = None, 0.0
     if e2e_steps:
         for _ in range(min(args.warmup, 2)):
             step_host()
-        barrier()
+        job.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             step_host()
         torch.cuda.synchronize()
-        dt_e2e = max_over_ranks(time.perf_counter() - t0)
-        barrier()
+        dt_e2e = job.max_over_ranks(time.perf_counter() - t0)
+        job.barrier()
         e2e = world * n * rows * cols * e2e_steps / dt_e2e / 1e6
-        # parity spot check of the timed outputs: device batch == host batch for frame 0
-        same = bool(torch.equal(d_out[0].cpu(), h_out[0]))
-
+    ccc = None
+    if cfg["wb"] == "ccc":  # the estimate of the last frame of the last call: shows the white balance did real work
+        ccc = {"uv_last_frame": list(p.ccc_uv()), "gains_bgr_last_frame": [float(g) for g in p.ccc_gains()],
+               "constructor_value": [128, 128]}
+        try:
+            resp = np.frombuffer(p.debug_table("ccc_response"), np.float64)
+            top = np.sort(resp)[-2:]
+            ccc["response_top1_minus_top2"] = float(top[1] - top[0])
+            ccc["response_range"] = float(resp.max() - resp.min())
+        except Exception as e:  # pragma: no cover
+            ccc["response_error"] = repr(e)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        job.finish()
         return
 
     # ---- parity of the timed outputs: first and last frame of the step against the cv2 oracle (checker only) ----
@@ -330,15 +402,10 @@ def run_b200(args):
     if not args.no_parity:
         step_device()
         torch.cuda.synchronize()
-        o = make_oracle(rows, cols)
-        nbad, maxd, checked = 0, 0, []
-        for i in sorted({0, n - 1}):
-            ref, _ = o.apply(frames[i], ENC)
-            got = d_out[i].cpu().numpy()
-            d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
-            nbad += int(np.count_nonzero(d)); maxd = max(maxd, int(d.max())); checked.append(i)
-        parity = {"frames_checked": len(checked), "frames": checked, "max_abs_diff": maxd, "differing_values": nbad,
-                  "against": "oracle/cv2_oracle.py (cv2 replay of the reference CPU path), device-resident output of the timed step"}
+        which = sorted({0, n - 1})
+        parity = check_parity(p, cfg, frames, {i: d_out[i].cpu().numpy() for i in which}, which)
+        if e2e_steps:
+            parity["host_path_equals_device_path"] = bool(torch.equal(d_out[0].cpu(), h_out[0]) and torch.equal(d_out[n - 1].cpu(), h_out[n - 1]))
 
     peak, peak_src = hbm_peak()
     n_fused = max(kernel_ms[4 + 2], 1.0)
@@ -350,15 +417,17 @@ def run_b200(args):
         return kernel_ms[i] / max(kernel_ms[4 + i], 1.0)
     px = float(n) * rows * cols
     other = {
-        # SURVEY 8d counts 14 B/px (3 gather + 8 fp32 map + 3 write); the kernel moves 11 (4-byte intermediate, packed map)
+        # SURVEY 8d counts 14 B/px (3 gather + 8 fp32 map + 3 write); the kernel is DESIGNED to move 11 (4-byte intermediate,
+        # packed 4-byte map, 3 B out): `moved_frac_of_peak` is the honest figure, `frac_of_peak` charges bytes it never moves
         "k_remap_tile": {"algorithmic_bytes_per_px": 14, "moved_bytes_per_px": 11, "avg_launch_ms": per_launch(3),
                          "achieved_gbs": 14 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None,
                          "moved_gbs": 11 * px / (per_launch(3) * 1e-3) / 1e9 if per_launch(3) > 0 else None},
-        "k_pca_stats": {"algorithmic_bytes_per_px": 1, "avg_launch_ms": per_launch(0),
-                        "achieved_gbs": px / (per_launch(0) * 1e-3) / 1e9 if per_launch(0) > 0 else None},
         "whole_step": {"algorithmic_bytes_per_px": 19, "ms": ms_total / args.steps,
                        "achieved_gbs": 19 * px / (ms_total / args.steps * 1e-3) / 1e9},
     }
+    if cfg["wb"] == "pca":
+        other["k_pca_stats"] = {"algorithmic_bytes_per_px": 1, "avg_launch_ms": per_launch(0),
+                                "achieved_gbs": px / (per_launch(0) * 1e-3) / 1e9 if per_launch(0) > 0 else None}
     for v in other.values():
         if v.get("achieved_gbs"):
             v["frac_of_peak"] = v["achieved_gbs"] / peak
@@ -366,42 +435,163 @@ def run_b200(args):
             v["moved_frac_of_peak"] = v["moved_gbs"] / peak
     if witness and witness.get("achieved_gbs"):
         witness["frac_of_peak"] = witness["achieved_gbs"] / peak
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_at_bench_size")
+            tj = json.load(f)
+        if args.config == 3 and n == 64:
+            traffic = tj.get("dram_bytes_per_launch_at_bench_size"); traffic_src = tj.get("source")
     except Exception:
         pass
+    ceiling = copy_ceiling(world)
+    d2h_gbs = 3.0 * world * n * rows * cols * e2e_steps / dt_e2e / 1e9 if e2e_steps else None
     line = {
         "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": n, "distribution": "N (natural-ish) + sensor cast",
+        "config": {"workload": cfg["workload"], "bench_config": args.config, "frames_per_step_per_gpu": n,
+                   "value_is": "device-resident throughput (inputs and outputs in HBM, CUDA events on the launching stream); "
+                               "the end-to-end number of the metric's name is e2e.value",
+                   "distribution": "N (natural-ish) + sensor cast; min(frames, 16) distinct frames per GPU, repeated to fill the batch",
                    "l2": f"inputs {n * rows * cols / 1e6:.0f} MB + outputs {3 * n * rows * cols / 1e6:.0f} MB per step >> 126 MB L2 "
-                         "(no flush needed)", "parallelism": f"frames sharded over {world} GPU(s), no collective", "host_numa_binding_rank0": numa,
-                   "kernel_ms_per_step": step_kernel_ms, "device_equals_host_path": same},
-        "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, bayer>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "(no flush needed)", "parallelism": f"frames sharded over {world} GPU(s), no collective", "host_numa_binding_rank0": job.numa,
+                   "kernel_ms_per_step": step_kernel_ms},
+        "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, Bayer -> 4-byte intermediate>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fused_ms,
                      "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)",
                      "other_kernels": other, "witness_debayer_gamma": witness},
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * rows * cols) * world,
                 "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "steps": e2e_steps,
-                "ms_per_step": dt_e2e / max(e2e_steps, 1) * 1e3,
+                "ms_per_step": dt_e2e / max(e2e_steps, 1) * 1e3, "d2h_gbs": d2h_gbs, "copy_ceiling_d2h_gbs": ceiling,
+                "frac_of_copy_ceiling": (d2h_gbs / ceiling) if (d2h_gbs and ceiling) else None,
                 "api": "rip_apply_batch_host (pinned host buffers, H2D + kernels + D2H inside the timed region, host wall clock)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "parity": parity,
     }
+    if ccc:
+        line["ccc"] = ccc
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = time_cpu_reference(rows, cols, args.cpu_frames, 1)
+        v, cores, dt = time_cpu_reference(cfg, args.cpu_frames, 1)
         import cv2
         line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_frames} frames of 4032x3040 through the cv2 call-for-call replay of the "
+                                "sample": f"{args.cpu_frames} frames of {cols}x{rows} through the cv2 call-for-call replay of the "
                                           f"reference CPU path (cv2 {cv2.__version__}, {cores} threads, {dt:.1f} s)"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    job.finish()
+    if parity and parity["differing_values"] != 0:
+        raise SystemExit("bench.py: the timed outputs differ from the oracle: " + json.dumps(parity))
+
+
+def run_latency(args, cfg):
+    """configs 2 and 4: frames one at a time.  A step = `--frames` consecutive single-frame calls of one camera stream."""
+    job = Job()
+    torch = job.torch
+    rank, world, local, dev = job.rank, job.world, job.local, job.dev
+    n, rows, cols, enc = args.frames, cfg["rows"], cfg["cols"], cfg["enc"]
+    p = make_pipeline(rows, cols, device=local, wb=cfg["wb"])
+    frames = make_frames(n, rows, cols, 3000 + 100 * rank, enc=enc)  # pageable numpy, like a caller's images
+    px = rows * cols
+    d_in = torch.from_numpy(frames).to(dev)
+    d_out = torch.empty((rows, cols, 3), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+
+    def step_device():  # one launch sequence (stats, lut, fused, remap) per frame, device-resident
+        for i in range(n):
+            p.process_batch_ptr(d_in[i].data_ptr(), 1, rows, cols, 1, enc, d_out.data_ptr(), host=False, stream=stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    job.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = p.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    job.barrier()
+    ms_total = job.max_over_ranks(ev0.elapsed_time(ev1))
+    launches = p.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n * px * args.steps / (ms_total * 1e-3) / 1e6
+    # kernel time alone (CUDA events around every kernel)
+    p._set_bool("profile/kernel_events", True)
+    step_device()
+    torch.cuda.synchronize()
+    kms = p._get_doubles("stats/kernel_ms")
+    p._set_bool("profile/kernel_events", False)
+    kernel_us_per_frame = float(sum(kms[:4])) / n * 1e3
+
+    # ---- end to end: RawImagePipeline::apply() frame by frame, pageable numpy in, numpy out -------
+    def timed_apply(steps):
+        lat = []
+        outs = {}
+        t_begin = time.perf_counter()
+        for s in range(steps):
+            for i in range(n):
+                t0 = time.perf_counter()
+                out = p.process(frames[i], enc)
+                lat.append((time.perf_counter() - t0) * 1e6)
+                if s == steps - 1 and i in (0, n - 1):
+                    outs[i] = out
+        return lat, outs, time.perf_counter() - t_begin
+
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
+    e2e, lat_graph, lat_plain, outs, dt_e2e = None, None, None, {}, 0.0
+    if e2e_steps:
+        timed_apply(1)  # warm-up: buffers, lazy tables, graph capture
+        job.barrier()
+        lat, outs, dt = timed_apply(e2e_steps)
+        dt_e2e = job.max_over_ranks(dt)
+        e2e = world * n * px * e2e_steps / dt_e2e / 1e6
+        lat_graph = percentiles(lat)
+        replays = p._get_int("stats/graph_replays")
+        if args.config == 2:  # the same without the CUDA-graph replay
+            p._set_bool("apply/cuda_graph", False)
+            timed_apply(1)
+            lat_plain = percentiles(timed_apply(e2e_steps)[0])
+            p._set_bool("apply/cuda_graph", True)
+    per_stream = job.gather({"rank": rank, "latency_us": lat_graph, "mpix_per_s": (n * px * e2e_steps / dt_e2e / 1e6) if e2e_steps else None})
+    if rank != 0:
+        job.finish()
+        return
+    parity = None
+    if not args.no_parity and outs:
+        parity = check_parity(p, cfg, frames, outs, sorted(outs))
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "bench_config": args.config, "frames_per_step_per_gpu": n,
+                   "value_is": "device-resident throughput of one-frame launch sequences (frames in HBM, CUDA events); "
+                               "the end-to-end number is e2e.value (RawImagePipeline::apply, pageable host arrays, one frame per call)",
+                   "distribution": "N (natural-ish) + sensor cast", "l2": "latency-bound: one 2 MP frame per call (fits L2)",
+                   "parallelism": f"one camera stream per GPU, {world} GPU(s), no collective", "host_numa_binding_rank0": job.numa},
+        "latency_us": {"kernels_only_per_frame": kernel_us_per_frame,
+                       "device_resident_call_per_frame": ms_total / args.steps / n * 1e3,
+                       "apply_host_to_host_cuda_graph": lat_graph, "apply_host_to_host_no_graph": lat_plain,
+                       "graph_replays": replays if e2e_steps else None},
+        "streams": per_stream,
+        "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * px) * world, "d2h_bytes_per_step": int(3 * n * px) * world,
+                "steps": e2e_steps, "ms_per_step": dt_e2e / max(e2e_steps, 1) * 1e3,
+                "api": "rip_apply (pageable host arrays -> pinned staging -> one CUDA-graph launch -> pinned staging -> host array)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "parity": parity,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, dt = time_cpu_reference(cfg, min(args.cpu_frames * 4, n), 1)
+        import cv2
+        line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                                "sample": f"{min(args.cpu_frames * 4, n)} frames of {cols}x{rows} through the cv2 call-for-call replay of the "
+                                          f"reference CPU path (cv2 {cv2.__version__}, {cores} threads, {dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    job.finish()
     if parity and parity["differing_values"] != 0:
         raise SystemExit("bench.py: the timed outputs differ from the oracle: " + json.dumps(parity))
 
@@ -412,7 +602,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per step per GPU (BASELINE configs[2]: 64)")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE configuration (SURVEY 8d); default 3 = configs[2]")
+    ap.add_argument("--frames", type=int, default=None, help="frames per step per GPU (default: the configuration's)")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames timed for cpu_baseline")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -421,12 +612,19 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed outputs")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.frames is None:
+        args.frames = cfg["frames"]
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
+    elif cfg["mode"] == "batch":
+        run_batch(args, cfg)
     else:
-        run_b200(args)
+        if args.steps > 5 and args.config == 4:
+            pass
+        run_latency(args, cfg)
 
 
 if __name__ == "__main__":

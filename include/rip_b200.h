@@ -100,7 +100,10 @@ RIP_API int rip_reset_white_balance_temporal_consistency(rip_pipeline* p);  /* r
  * Development switches (bool): profile/kernel_events (CUDA events around every kernel launch),
  *   debug/force_generic_kernels (skip the TMA fast path), debug/force_float_map (undistortion reads the fp32 map
  *   instead of the packed fixed-point one), debug/force_gather_remap (undistortion gathers from global memory instead
- *   of the TMA-staged tile kernel).  None of them changes a single output byte.                               */
+ *   of the TMA-staged tile kernel); (int) debug/fused_kernel: 0 = the measured choice per stage set, 1 = tile kernel,
+ *   2 = strip kernel.  None of them changes a single output byte.
+ * Extension (bool): undistortion/rect_mask -- getRectMask() returns a real validity mask (u8, 255 where all four taps of
+ *   the bilinear remap lie inside the source image) instead of the reference's never-written empty image.        */
 RIP_API int rip_set_bool(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_int(rip_pipeline* p, const char* key, int value);
 RIP_API int rip_set_double(rip_pipeline* p, const char* key, double value);
@@ -147,6 +150,17 @@ RIP_API int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t 
 RIP_API int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames,
                          int rows, int cols, int channels, const char* encoding, uint8_t* out,
                          size_t out_frame_stride);
+
+/* Host-to-host over several GPUs of one box (frames are independent, so they shard with no collective):
+ * `handles[i]` is a pipeline bound to its own device (rip_set_device) and configured like the others.  The batch is cut
+ * into n_handles contiguous chunks (sizes differ by at most one frame; chunk i goes to handles[i]); every chunk runs
+ * rip_apply_batch_host on its own host thread; returns when `out` is complete.  With CCC temporal consistency a batch
+ * is ONE camera stream and must go to one pipeline: the call then fails with RIP_ERR_INVALID_ARGUMENT.  Returns the
+ * first failing chunk's status (its message is in that handle's rip_last_error).  The reference has no multi-GPU path
+ * (raw_image_pipeline.cpp:193-196 uploads to the one current device).                                             */
+RIP_API int rip_apply_batch_host_multi(rip_pipeline* const* handles, int n_handles, const uint8_t* in, size_t in_frame_stride,
+                               int n_frames, int rows, int cols, int channels, const char* encoding, uint8_t* out,
+                               size_t out_frame_stride);
 
 /* ---- inspection ---------------------------------------------------------------------------
  * Host-computed tables exactly as the kernels consume them (no GPU needed): "gamma_lut" (256 B,

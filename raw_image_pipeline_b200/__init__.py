@@ -5,6 +5,7 @@ The pixel work is done by hand-written CUDA kernels in ``librip_b200.so`` (C ABI
 ``include/rip_b200.h``); this package is the Python face of that library, mirroring the
 reference's pybind module ``py_raw_image_pipeline``.
 """
+from .multi_gpu import MultiGpuPipeline  # noqa: F401
 from .pipeline import RawImagePipeline, RawImagePipelineError  # noqa: F401
 
-__all__ = ["RawImagePipeline", "RawImagePipelineError"]
+__all__ = ["RawImagePipeline", "RawImagePipelineError", "MultiGpuPipeline"]

@@ -93,4 +93,45 @@ __device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRo
   Bw = row_has_r ? other_colour : row_colour;
 }
 
+// ---- the same for a rolled row loop: the phase of the current centre row is kept in registers and flipped per row ------
+// (five one-cycle operations per row; used where unrolling the row loop would overflow the instruction cache)
+struct BayerPhaseRT {
+  uint32_t own, other;  // lane selectors of the CENTRE row (its bottom row uses them swapped)
+  uint32_t sel, site;
+  bool row_has_r;
+  __device__ __forceinline__ void flip() {
+    own ^= 0x0101u; other ^= 0x0101u;  // 0x4240 <-> 0x4341
+    sel ^= 0x5454u;                    // 0x7250 <-> 0x2604
+    site = ~site;
+    row_has_r = !row_has_r;
+  }
+};
+__device__ __forceinline__ BayerPhaseRT bayer_phase_rt(int centre_row, int cfa) {
+  const BayerPhase q = bayer_phase(centre_row, cfa);
+  BayerPhaseRT r;
+  r.own = q.own; r.other = q.other; r.sel = q.sel_e; r.site = q.site; r.row_has_r = q.row_has_r;
+  return r;
+}
+// the row BELOW a centre row of phase q
+__device__ __forceinline__ BayerRow load_bayer_row_below(const uint32_t* p, const BayerPhaseRT& q) {
+  const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+  BayerRow b;
+  b.c = w1; b.l = funnel_r(w0, w1, 24); b.r = funnel_r(w1, w2, 8);
+  b.A = prmt(b.c, 0u, q.own);
+  b.S = prmt(b.l, 0u, q.own) + prmt(b.r, 0u, q.own);
+  b.W = prmt(b.l, 0u, q.other) + prmt(b.r, 0u, q.other) + 0x00020002u;
+  return b;
+}
+__device__ __forceinline__ void demosaic_window(const BayerRow& n, const BayerRow& m, const BayerRow& s, const BayerPhaseRT& q,
+                                                uint32_t& Bw, uint32_t& Gw, uint32_t& Rw) {
+  const uint32_t H = avg_round_u8x4(m.l, m.r), V = avg_round_u8x4(n.c, s.c);
+  const uint32_t X = ((n.A + s.A + m.W) >> 2) & 0x00ff00ffu;
+  const uint32_t D = ((n.S + s.S + 0x00020002u) >> 2) & 0x00ff00ffu;
+  Gw = prmt(X, m.c, q.sel);
+  const uint32_t row_colour = (m.c & q.site) | (H & ~q.site);
+  const uint32_t other_colour = prmt(D, V, q.sel);
+  Rw = q.row_has_r ? row_colour : other_colour;
+  Bw = q.row_has_r ? other_colour : row_colour;
+}
+
 }  // namespace rip

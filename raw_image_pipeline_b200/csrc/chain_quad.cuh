@@ -3,37 +3,47 @@
 // kernels run and what tests/test_pixel_math_host.py checks exhaustively against cv2; tests/test_chain_quad_host.py checks
 // this file against chain_pixel() over the whole 2^24 colour cube for every stage set.
 //
-// What differs from chain_pixel():
+// The full chain is bound by instruction issue; what this form saves over chain_pixel():
 //   * inputs stay packed (byte k of Bw/Gw/Rw = pixel k); a channel that needs no table (no white balance, or the G
 //     channel under pca) becomes the float 2^23 + v with ONE byte permute (then one subtraction: no conversion pipe);
-//   * white-balance tables are bytes (their entries are 0..255), a quarter of the bank conflicts of the float form;
-//   * a zero bias is skipped (adding +0.0f changes nothing that survives the u8 conversion);
-//   * float(L) is built as (v >> 15) | 0x4B000000 by one funnel shift; the sRGB table holds 2 G + 1, which makes the
-//     rounding constant of the XYZ descale implicit (matrix rows sum to 4096);
-//   * LabToYF entries carry the constants of abToXZ_b ({y | (ify - 4194) << 16, ify + 10484});
-//   * sdiv[v] and the value-gain float share one 64-bit entry; 3-input min/max;
-//   * HSV2BGR's four candidates are gathered with three byte permutes (the hue entry's selector indexes {t0 t1 . . t2 t3}).
+//   * table addresses are explicit 32-bit shared-window addresses (see `taddr`): indices are merged into aligned table
+//     bases by the instruction that masks / extracts them, so no lookup pays a separate base addition;
+//   * BGR -> Lab: the sRGB table holds 2 G + 1; the rows of the XYZ matrix sum to 4096, which makes the rounding constant
+//     of the descale implicit; float(L) is built as (v >> 15) | 0x4B000000 by one funnel shift;
+//   * Lab -> BGR: the LabToYF entry of L' (one 128-bit load) carries y already multiplied by the three matrix coefficients
+//     (+ the rounding constant) and both abToXZ offsets;
+//   * sdiv[v] and the value-gain float share one 64-bit entry; 3-input min/max; HSV2BGR's four candidates are gathered
+//     with three byte permutes; a zero bias is not added.
+// Measured and rejected (profiles/r2_strip_kernel.md): 128-bit per-channel PRODUCT tables for the colour calibration and
+// for the XYZ dot products cut 30 instructions per pixel but triple the shared-memory wavefronts (random 16-byte entries
+// conflict 2-3 ways): the kernel becomes shared-memory bound, 9.3 vs 5.5 ms per 64 x 12 MP.
 #pragma once
 #include "pixel_math.cuh"
 
 namespace rip {
 
-struct alignas(8) Pair32 { uint32_t x, y; };  // one 64-bit shared-memory load
+struct alignas(8) Pair32 { uint32_t x, y; };          // one 64-bit shared-memory load
+struct alignas(16) Quad32 { uint32_t x, y, z, w; };    // one 128-bit shared-memory load
 
 // Table addresses.  On the device they are 32-bit shared-window addresses and every lookup is an explicit ld.shared, so
 // that the address arithmetic is exactly what is written here (the compiler otherwise adds the window base with a
 // separate instruction per lookup): a byte index is merged into a 256-byte aligned base by the byte permute that extracts
-// it, a masked index is OR-ed into a 4096-byte aligned base by the same LOP3 that masks it.  On the host (test build)
-// they are byte pointers.
+// it, a masked index is OR-ed into an aligned base by the same LOP3 that masks it.  On the host (test build) they are
+// byte pointers.
 #if defined(__CUDA_ARCH__)
 typedef uint32_t taddr;
 RIP_HD uint32_t lds_u8(taddr a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 RIP_HD uint32_t lds_u16(taddr a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 RIP_HD uint32_t lds_u32(taddr a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 RIP_HD Pair32 lds_u64(taddr a) { Pair32 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+RIP_HD Quad32 lds_u128(taddr a) {
+  Quad32 v;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 // base + byte K of w; base % 256 == 0
 template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return prmt(w, base, 0x7650u + K); }
-// base + (v & mask); base % 4096 == 0, mask < 4096
+// base + (v & mask); base % (mask + 1 rounded up to a power of two) == 0
 RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return (v & mask) | base; }
 #else
 typedef const uint8_t* taddr;
@@ -41,9 +51,14 @@ RIP_HD uint32_t lds_u8(taddr a) { return *a; }
 RIP_HD uint32_t lds_u16(taddr a) { uint16_t v; memcpy(&v, a, 2); return v; }
 RIP_HD uint32_t lds_u32(taddr a) { uint32_t v; memcpy(&v, a, 4); return v; }
 RIP_HD Pair32 lds_u64(taddr a) { Pair32 v; memcpy(&v, a, 8); return v; }
+RIP_HD Quad32 lds_u128(taddr a) { Quad32 v; memcpy(&v, a, 16); return v; }
 template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return base + ((w >> (8 * K)) & 255u); }
 RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return base + (v & mask); }
 #endif
+// base + 4 * byte K of w (a table of 32-bit entries); base % 1024 == 0
+template <int K> RIP_HD taddr taddr_byte4(taddr base, uint32_t w) {
+  return taddr_masked(base, K == 0 ? (w << 2) : (w >> (8 * K - 2)), 0x3fcu);
+}
 
 #if defined(__CUDACC__)
 // table address of a shared-memory pointer (device code; the host branch only serves nvcc's host pass, which parses kernels)
@@ -56,18 +71,19 @@ __device__ __forceinline__ taddr taddr_of_shared(const void* p) {
 }
 #endif
 
-// tables of the strip kernel (chain_tables.hpp build_strip_blob lays them out)
+// tables of the strip kernel (chain_tables.hpp lays them out: SOFF_*)
 struct StripTables {
-  taddr wb_b, wb_g, wb_r;  // u8[256] each, 256-byte aligned: per-frame white-balance LUTs
   taddr gamma;             // u8[256]
-  taddr inv_g;             // u8[4096]  sRGBInvGammaTab_b
+  taddr wb_b, wb_g, wb_r;  // u8[256] each, 256-byte aligned: per-frame white-balance LUTs (stage sets without colour calibration)
+  taddr wbf_b, wbf_g, wbf_r;  // f32[256] each, 1024-byte aligned: the same as floats (stage sets with colour calibration)
   taddr g2;                // u16[256]  2 * sRGBGammaTab_b[gamma[x]] + 1
-  taddr lab_c;             // u16[2048] LabCbrtTab_b, 4096-byte aligned
-  taddr yf2;               // {u32,u32}[256]  x = y | (ify - 4194) << 16 (signed high half), y = ify + 10484
-  taddr sv;                // {u32,u32}[256]  x = sdiv[v], y = float bits of (value gain lut)[v] * (1/255f)
+  taddr sf;                // f32[256], 1024-byte aligned
   taddr hdiv;              // i32[256]
+  taddr sv;                // {u32,u32}[256]  x = sdiv[v], y = float bits of (value gain lut)[v] * (1/255f)
   taddr hue;               // HueEntry[288], selector for prmt({t0 t1 0 0}, {t2 t3 0 0})
-  taddr sf;                // f32[256]
+  taddr lab_c;             // u16[2048] LabCbrtTab_b, 4096-byte aligned
+  taddr inv_g;             // u8[4096]  sRGBInvGammaTab_b
+  taddr yf4;               // {i32 x4}[256]: -6296 y + 8192, 7684 y + 8192, -836 y + 8192, (ify - 4194) << 16 | (ify + 10484)
 };
 
 RIP_HD float bits_to_float(uint32_t u) {
@@ -102,48 +118,38 @@ RIP_HD uint32_t funnel_shift_r(uint32_t lo, uint32_t hi, int shift) {
 // float 2^23 + byte K of `w` (exact): bytes {w.K, 00, 00, 4B}
 template <int K>
 RIP_HD float biased_float_of_byte(uint32_t w) { return bits_to_float(prmt(w, 0x4B000000u, 0x7650u + K)); }
-RIP_HD float biased_float_of_u8(uint32_t v) { return bits_to_float(v | 0x4B000000u); }
 
 // TAIL: the pixel lies in cv2's scalar row tail of HSV2BGR (columns >= width & ~31), which rounds where the vector loop
-// truncates (pixel_math.cuh hsv_gain_to_bgr)
-// WBG: the G channel has a white-balance table too (ccc; pca leaves G untouched).  BIAS: the colour calibration has a
-// non-zero bias (the strip kernel leaves such configurations to the tile kernel, so its instantiations carry no bias add).
-template <uint32_t STAGES, int K, bool TAIL = false, bool WBG = true, bool BIAS = true>
+// truncates (pixel_math.cuh hsv_gain_to_bgr).  WBG: the G channel has a white-balance table too (ccc; pca leaves G
+// untouched).  A colour calibration with a non-zero bias is not handled here (the strip kernel leaves such
+// configurations to the tile kernel, so no instantiation carries a bias add).
+template <uint32_t STAGES, int K, bool TAIL = false, bool WBG = true>
 RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, const ChainConsts& k, const StripTables& t) {
-  int b, g, r;
+  int b = 0, g = 0, r = 0;
   if (STAGES & ST_CC) {
-    float xb, xg, xr;  // 2^23 + channel value
-    if (STAGES & ST_WB) {  // white_balance.cpp:117-127 (pca) / ccc.cpp:383-386: per-frame byte LUTs
-      xb = biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_b, Bw)));
-      xr = biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_r, Rw)));
-      xg = WBG ? biased_float_of_u8(lds_u8(taddr_byte<K>(t.wb_g, Gw))) : biased_float_of_byte<K>(Gw);
-    } else {
-      xb = biased_float_of_byte<K>(Bw); xg = biased_float_of_byte<K>(Gw); xr = biased_float_of_byte<K>(Rw);
+    float fb, fg, fr;
+    if (STAGES & ST_WB) {  // white_balance.cpp:117-127 (pca) / ccc.cpp:383-386: per-frame LUTs, kept as floats
+      fb = bits_to_float(lds_u32(taddr_byte4<K>(t.wbf_b, Bw)));
+      fr = bits_to_float(lds_u32(taddr_byte4<K>(t.wbf_r, Rw)));
+      fg = WBG ? bits_to_float(lds_u32(taddr_byte4<K>(t.wbf_g, Gw))) : RIP_FSUB(biased_float_of_byte<K>(Gw), 8388608.0f);
+    } else {  // (float)v = (2^23 + v) - 2^23 exactly
+      fb = RIP_FSUB(biased_float_of_byte<K>(Bw), 8388608.0f); fg = RIP_FSUB(biased_float_of_byte<K>(Gw), 8388608.0f);
+      fr = RIP_FSUB(biased_float_of_byte<K>(Rw), 8388608.0f);
     }
-    // (float)v = (2^23 + v) - 2^23 exactly; the nine matrix entries stay constant-bank operands of the multiplies (a fused
-    // fma(2^23 + v, M, -2^23 M) form saves these three subtractions but needs nine more live registers -- measured: spills)
-    const float fb = RIP_FSUB(xb, 8388608.0f), fg = RIP_FSUB(xg, 8388608.0f), fr = RIP_FSUB(xr, 8388608.0f);
+    // cv::gemm on N x 3 fp32 == separately rounded products, summed left to right; the nine matrix entries
+    // are constant-bank operands of the multiplies
     float y[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float t0 = RIP_FMUL(fb, k.cc[3 * j + 0]);
-      const float t1 = RIP_FMUL(fg, k.cc[3 * j + 1]);
-      const float t2 = RIP_FMUL(fr, k.cc[3 * j + 2]);
-      y[j] = RIP_FADD(RIP_FADD(t0, t1), t2);
-    }
-    if (BIAS) {  // cv::add with the bias Scalar
-      y[0] = RIP_FADD(y[0], k.cc_bias[0]); y[1] = RIP_FADD(y[1], k.cc_bias[1]); y[2] = RIP_FADD(y[2], k.cc_bias[2]);
-    }
+    for (int j = 0; j < 3; ++j)
+      y[j] = RIP_FADD(RIP_FADD(RIP_FMUL(fb, k.cc[3 * j + 0]), RIP_FMUL(fg, k.cc[3 * j + 1])), RIP_FMUL(fr, k.cc[3 * j + 2]));
     b = sat_u8_rint(y[0]); g = sat_u8_rint(y[1]); r = sat_u8_rint(y[2]);
+  } else if (STAGES & ST_WB) {
+    b = (int)lds_u8(taddr_byte<K>(t.wb_b, Bw)); r = (int)lds_u8(taddr_byte<K>(t.wb_r, Rw));
+    g = WBG ? (int)lds_u8(taddr_byte<K>(t.wb_g, Gw)) : (int)prmt(Gw, 0u, 0x4440u + K);
   } else {
-    if (STAGES & ST_WB) {
-      b = (int)lds_u8(taddr_byte<K>(t.wb_b, Bw)); r = (int)lds_u8(taddr_byte<K>(t.wb_r, Rw));
-      g = WBG ? (int)lds_u8(taddr_byte<K>(t.wb_g, Gw)) : (int)prmt(Gw, 0u, 0x4440u + K);
-    } else {
-      b = (int)prmt(Bw, 0u, 0x4440u + K); g = (int)prmt(Gw, 0u, 0x4440u + K); r = (int)prmt(Rw, 0u, 0x4440u + K);
-    }
+    b = (int)prmt(Bw, 0u, 0x4440u + K); g = (int)prmt(Gw, 0u, 0x4440u + K); r = (int)prmt(Rw, 0u, 0x4440u + K);
   }
-  if (STAGES & ST_VIG) {  // vignetting_correction.cpp:68-93; gamma (if enabled) is folded into t.g2
+  if (STAGES & ST_VIG) {  // vignetting_correction.cpp:68-93; gamma (if enabled) is folded into the forward tables
     // t.g2 holds 2 G + 1 (G = sRGBGammaTab_b entry): every row of the XYZ matrix sums to 4096, so
     // sum c_i (2 G_i + 1) = 2 (sum c_i G_i + 2048) -- the rounding constant of the descale comes for free, and
     // LabCbrtTab_b[(dot + 2048) >> 12] sits at byte offset 2 * index = (sum >> 12) & 0x1ffe (sum < 2^25)
@@ -157,18 +163,17 @@ RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, cons
     const int Lp = sat_u8_rint(RIP_FMUL(RIP_FSUB(xL, 8388608.0f), mask));
     const int A = (500 * (fX - fY) + 4210688) >> 15;   // 128 * 32768 + 16384
     const int B = (200 * (fY - fZ) + 4210688) >> 15;
-    const Pair32 yf = lds_u64(t.yf2 + 8 * Lp);
-    const int yy = (int)(yf.x & 0xffffu);
-    const int fx = ((int)yf.x >> 16) + ((A * 268435 + 128) >> 13);
-    const int fz = (int)yf.y - ((B * 41943 + 16) >> 9);
+    const Quad32 yf = lds_u128(t.yf4 + 16 * Lp);
+    const int fx = ((int)yf.w >> 16) + ((A * 268435 + 128) >> 13);
+    const int fz = (int)(yf.w & 0xffffu) - ((B * 41943 + 16) >> 9);
     int x = lab_xz_cubic(fx), z = lab_xz_cubic(fz);
     if ((fx < fz ? fx : fz) <= 3390) {  // dark pixels only
       if (fx <= 3390) x = lab_xz_linear(fx);
       if (fz <= 3390) z = lab_xz_linear(fz);
     }
-    int ro = (12615 * x - 6296 * yy - 2223 * z + 8192) >> 14;
-    int go = (-3773 * x + 7684 * yy + 185 * z + 8192) >> 14;
-    int bo = (217 * x - 836 * yy + 4715 * z + 8192) >> 14;
+    int ro = (12615 * x + (int)yf.x - 2223 * z) >> 14;
+    int go = (-3773 * x + (int)yf.y + 185 * z) >> 14;
+    int bo = (217 * x + (int)yf.z + 4715 * z) >> 14;
     ro = ro < 0 ? 0 : (ro > 4095 ? 4095 : ro);
     go = go < 0 ? 0 : (go > 4095 ? 4095 : go);
     bo = bo < 0 ? 0 : (bo > 4095 ? 4095 : bo);
@@ -180,13 +185,14 @@ RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, cons
     const int vmax = max3i(b, g, r), vmin = min3i(b, g, r);
     const int d = vmax - vmin;
     const Pair32 sv = lds_u64(t.sv + 8 * vmax);
-    const int s = (d * (int)sv.x + 2048) >> 12;
     int hh = r - g + 4 * d;
     if (vmax == g) hh = b - r + 2 * d;
     if (vmax == r) hh = g - b;
     const int h = (hh * (int)lds_u32(t.hdiv + 4 * d) + 2048) >> 12;  // -30 .. 150, wrapped by the table
     const Pair32 he = lds_u64(t.hue + 8 * (h + HUE_BIAS));             // HueEntry {f, sel}
-    const float f = bits_to_float(he.x), sf = bits_to_float(lds_u32(t.sf + 4 * s)), vf = bits_to_float(sv.y);
+    // s = (d * sdiv[v] + 2048) >> 12 in 0..255: the float table entry sits at byte offset 4 s = ((..) >> 10) & 0x3fc
+    const float sf = bits_to_float(lds_u32(taddr_masked(t.sf, (uint32_t)(d * (int)sv.x + 2048) >> 10, 0x3fcu)));
+    const float f = bits_to_float(he.x), vf = bits_to_float(sv.y);
     const float t1 = RIP_FMUL(vf, RIP_FSUB(1.0f, sf));
     const float t2 = RIP_FMUL(vf, RIP_FMA(-sf, f, 1.0f));
     const float t3 = RIP_FMUL(vf, RIP_FMA(-sf, RIP_FSUB(1.0f, f), 1.0f));
@@ -203,12 +209,12 @@ RIP_HD uint32_t chain_px(uint32_t Bw, uint32_t Gw, uint32_t Rw, float mask, cons
   return pack_bgr(b, g, r);
 }
 
-template <uint32_t STAGES, bool WBG = true, bool BIAS = true>
+template <uint32_t STAGES, bool WBG = true>
 RIP_HD void chain_quad(uint32_t Bw, uint32_t Gw, uint32_t Rw, const float m[4], const ChainConsts& k, const StripTables& t, uint32_t px[4]) {
-  px[0] = chain_px<STAGES, 0, false, WBG, BIAS>(Bw, Gw, Rw, m[0], k, t);
-  px[1] = chain_px<STAGES, 1, false, WBG, BIAS>(Bw, Gw, Rw, m[1], k, t);
-  px[2] = chain_px<STAGES, 2, false, WBG, BIAS>(Bw, Gw, Rw, m[2], k, t);
-  px[3] = chain_px<STAGES, 3, false, WBG, BIAS>(Bw, Gw, Rw, m[3], k, t);
+  px[0] = chain_px<STAGES, 0, false, WBG>(Bw, Gw, Rw, m[0], k, t);
+  px[1] = chain_px<STAGES, 1, false, WBG>(Bw, Gw, Rw, m[1], k, t);
+  px[2] = chain_px<STAGES, 2, false, WBG>(Bw, Gw, Rw, m[2], k, t);
+  px[3] = chain_px<STAGES, 3, false, WBG>(Bw, Gw, Rw, m[3], k, t);
 }
 
 }  // namespace rip

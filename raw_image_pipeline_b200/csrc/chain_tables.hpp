@@ -95,43 +95,38 @@ inline void build_chain_blob(const ChainTableParams& q, uint8_t* blob) {
 }
 
 // ---- tables of the strip kernel (chain_quad.cuh StripTables) ---------------------------------------------------
-// Byte offsets; the kernel copies the blob verbatim into 4096-byte aligned shared memory, and chain_quad.cuh relies on
-// SOFF_LABC % 4096 == 0 and SOFF_WB % 256 == 0.  The SOFF_WB region is a hole in the blob: per-frame data.
+// Byte offsets; the kernel copies the static parts of the blob verbatim into 4096-byte aligned shared memory, ordered so
+// that a stage set needs a prefix: gamma only -> 256 B, + white balance -> 1 KB, + enhancer -> 7.25 KB, + vignetting ->
+// 21 KB, + colour calibration after white balance -> 24 KB.  chain_quad.cuh relies on the alignments noted.  SOFF_WB and
+// SOFF_WBF are holes in the blob: per-frame data the kernel fills.
 enum : int {
-  SOFF_LABC = 0,        // u16[2048]
-  SOFF_INVG = 4096,     // u8[4096]
-  SOFF_WB = 8192,       // u8[3][256]      per-frame white-balance LUTs B, G, R (filled by the kernel)
-  SOFF_GAMMA = 8960,    // u8[256]
-  SOFF_G2 = 9216,       // u16[256]        2 * sRGBGammaTab_b[gamma[x]] + 1
-  SOFF_YF2 = 9728,      // {u32, u32}[256]  x = y | (ify - 4194) << 16, y = ify + 10484
-  SOFF_SV = 11776,      // {u32, u32}[256]  x = sdiv[v], y = float bits of the value-gain entry
-  SOFF_HDIV = 13824,    // i32[256]
-  SOFF_HUE = 14848,     // HueEntry[288], selector over {t0 t1 0 0 | t2 t3 0 0}
-  SOFF_SF = 17152,      // f32[256]
-  STRIP_TABLE_BYTES = 18176
+  SOFF_GAMMA = 0,       // u8[256]
+  SOFF_WB = 256,        // u8[3][256]       per-frame white-balance LUTs B, G, R (256-byte aligned)
+  SOFF_SF = 1024,       // f32[256]         (1024-byte aligned)
+  SOFF_HDIV = 2048,     // i32[256]
+  SOFF_SV = 3072,       // {u32, u32}[256]  x = sdiv[v], y = float bits of the value-gain entry
+  SOFF_HUE = 5120,      // HueEntry[288], selector over {t0 t1 0 0 | t2 t3 0 0}
+  SOFF_LABC = 8192,     // u16[2048]        (4096-byte aligned)
+  SOFF_INVG = 12288,    // u8[4096]
+  SOFF_YF4 = 16384,     // {i32 x4}[256]    -6296 y + 8192, 7684 y + 8192, -836 y + 8192, (ify - 4194) << 16 | (ify + 10484)
+  SOFF_G2 = 20480,      // u16[256]         2 * sRGBGammaTab_b[gamma[x]] + 1
+  SOFF_WBF = 21504,     // f32[3][256]      per-frame white-balance LUTs as floats (1024-byte aligned each)
+  STRIP_TABLE_BYTES = 24576,
+  STRIP_BLOB_BYTES = 21504,  // the blob ends where the per-frame float tables start
+  STRIP_ENH_END = 7424,
+  STRIP_VIG_END = 20992
 };
 
 // `blob`: the legacy blob of the same parameters (build_chain_blob)
 inline void build_strip_blob(const uint8_t* blob, uint8_t* sblob) {
-  memset(sblob, 0, STRIP_TABLE_BYTES);
+  memset(sblob, 0, STRIP_BLOB_BYTES);
   memcpy(sblob + SOFF_GAMMA, blob + OFF_GAMMA, 256);
-  memcpy(sblob + SOFF_INVG, blob + OFF_INVG, 4096);
-  const uint16_t* g2 = reinterpret_cast<const uint16_t*>(blob + OFF_G2);
-  uint16_t* g2s = reinterpret_cast<uint16_t*>(sblob + SOFF_G2);
-  for (int i = 0; i < 256; ++i) g2s[i] = (uint16_t)(2 * g2[i] + 1);  // <= 4081
-  memcpy(sblob + SOFF_LABC, blob + OFF_LABC, 4096);
-  const uint32_t* yf = reinterpret_cast<const uint32_t*>(blob + OFF_YF);
-  uint32_t* yf2 = reinterpret_cast<uint32_t*>(sblob + SOFF_YF2);
-  for (int i = 0; i < 256; ++i) {
-    const int y = (int)(yf[i] & 0xffffu), ify = (int)(yf[i] >> 16);
-    yf2[2 * i] = (uint32_t)y | ((uint32_t)(uint16_t)(int16_t)(ify - 4194) << 16);  // fx = ify + adiv, adiv = (..) - 4194
-    yf2[2 * i + 1] = (uint32_t)(ify + 10484);                                       // fz = ify - bdiv, bdiv = (..) - 10485 + 1
-  }
+  memcpy(sblob + SOFF_SF, blob + OFF_SF, 1024);
+  memcpy(sblob + SOFF_HDIV, blob + OFF_HDIV, 1024);
   const int32_t* sdiv = reinterpret_cast<const int32_t*>(blob + OFF_SDIV);
   const uint32_t* vf = reinterpret_cast<const uint32_t*>(blob + OFF_VF);
   uint32_t* sv = reinterpret_cast<uint32_t*>(sblob + SOFF_SV);
   for (int i = 0; i < 256; ++i) { sv[2 * i] = (uint32_t)sdiv[i]; sv[2 * i + 1] = vf[i]; }
-  memcpy(sblob + SOFF_HDIV, blob + OFF_HDIV, 1024);
   const HueEntry* hue = reinterpret_cast<const HueEntry*>(blob + OFF_HUE);
   HueEntry* hue2 = reinterpret_cast<HueEntry*>(sblob + SOFF_HUE);
   for (int i = 0; i < 256 + HUE_BIAS; ++i) {
@@ -141,7 +136,20 @@ inline void build_strip_blob(const uint8_t* blob, uint8_t* sblob) {
     for (int n = 0; n < 4; ++n) sel |= remap[(hue[i].sel >> (4 * n)) & 7u] << (4 * n);
     hue2[i].f = hue[i].f; hue2[i].sel = sel;
   }
-  memcpy(sblob + SOFF_SF, blob + OFF_SF, 1024);
+  memcpy(sblob + SOFF_LABC, blob + OFF_LABC, 4096);
+  memcpy(sblob + SOFF_INVG, blob + OFF_INVG, 4096);
+  const uint32_t* yf = reinterpret_cast<const uint32_t*>(blob + OFF_YF);
+  int32_t* yf4 = reinterpret_cast<int32_t*>(sblob + SOFF_YF4);
+  for (int i = 0; i < 256; ++i) {
+    const int y = (int)(yf[i] & 0xffffu), ify = (int)(yf[i] >> 16);
+    // Lab2RGB: (c_x x + c_y y + c_z z + 8192) >> 14 with c_y = -6296 / 7684 / -836 for R / G / B
+    yf4[4 * i + 0] = -6296 * y + 8192; yf4[4 * i + 1] = 7684 * y + 8192; yf4[4 * i + 2] = -836 * y + 8192;
+    // fx = ify + adiv, adiv = (..) - 4194;  fz = ify - bdiv, bdiv = (..) - 10485 + 1
+    yf4[4 * i + 3] = (int32_t)(((uint32_t)(uint16_t)(int16_t)(ify - 4194) << 16) | (uint32_t)(ify + 10484));
+  }
+  const uint16_t* g2 = reinterpret_cast<const uint16_t*>(blob + OFF_G2);
+  uint16_t* g2s = reinterpret_cast<uint16_t*>(sblob + SOFF_G2);
+  for (int i = 0; i < 256; ++i) g2s[i] = (uint16_t)(2 * g2[i] + 1);  // <= 4081
 }
 
 // pointers into a blob (host memory or shared memory); wbf is set by the caller
@@ -175,18 +183,14 @@ inline
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-StripTables strip_tables_at(taddr t) {  // t: address of the blob copy (device: shared-window address, 4096-byte aligned)
+StripTables strip_tables_at(taddr t) {  // t: address of the table block (device: shared-window address, 4096-byte aligned)
   StripTables c;
-  c.wb_b = t + SOFF_WB; c.wb_g = t + (SOFF_WB + 256); c.wb_r = t + (SOFF_WB + 512);
   c.gamma = t + SOFF_GAMMA;
-  c.inv_g = t + SOFF_INVG;
+  c.wb_b = t + SOFF_WB; c.wb_g = t + (SOFF_WB + 256); c.wb_r = t + (SOFF_WB + 512);
+  c.sf = t + SOFF_SF; c.hdiv = t + SOFF_HDIV; c.sv = t + SOFF_SV; c.hue = t + SOFF_HUE;
+  c.lab_c = t + SOFF_LABC; c.inv_g = t + SOFF_INVG; c.yf4 = t + SOFF_YF4;
   c.g2 = t + SOFF_G2;
-  c.lab_c = t + SOFF_LABC;
-  c.yf2 = t + SOFF_YF2;
-  c.sv = t + SOFF_SV;
-  c.hdiv = t + SOFF_HDIV;
-  c.hue = t + SOFF_HUE;
-  c.sf = t + SOFF_SF;
+  c.wbf_b = t + SOFF_WBF; c.wbf_g = t + (SOFF_WBF + 1024); c.wbf_r = t + (SOFF_WBF + 2048);
   return c;
 }
 

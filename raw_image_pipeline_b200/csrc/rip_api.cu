@@ -2,15 +2,21 @@
 // device-resident tables, and orchestrates  stats -> LUT -> fused -> remap  per batch of frames.
 // There is no CPU pixel path in this library: without a CUDA device every pixel call fails.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
 
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rip_b200.h"
@@ -59,6 +65,88 @@ struct FrameGeom {
   std::string out_encoding;
 };
 
+// memcpy that leaves the lines of the PINNED side (`pinned`: dst or src) in the last-level cache only: every 64-byte line is
+// demoted (CLDEMOTE, a hint: a no-op where unsupported) after use.  The DMA engine of the GPU reads / overwrites that
+// buffer next, and snooping lines out of eight cores' private L2s slowed the device-side copies 4-5x (measured: 1014 vs
+// 213 us for H2D + kernels + D2H of a 1080p frame, profiles/r2_apply_latency.md).
+inline void demote_range(const uint8_t* p, size_t n) {
+#if defined(__x86_64__)
+  for (const uint8_t* q = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)63); q < p + n; q += 64)
+    asm volatile(".byte 0x0f, 0x1c, 0x07" ::"D"(q) : "memory");  // cldemote (%rdi)
+#else
+  (void)p; (void)n;
+#endif
+}
+inline void copy_and_demote(uint8_t* dst, const uint8_t* src, size_t n, int pinned_side /* 0: dst, 1: src */) {
+  const size_t kBlock = 16 << 10;
+  for (size_t o = 0; o < n; o += kBlock) {
+    const size_t m = std::min(kBlock, n - o);
+    memcpy(dst + o, src + o, m);
+    demote_range(pinned_side ? src + o : dst + o, m);
+  }
+}
+
+// A few persistent host threads that copy between the caller's (pageable) images and the pipeline's pinned staging
+// buffers: one thread moves ~10 GB/s, a 1080p BGR8 frame is 6.2 MB, and the copies would otherwise dominate rip_apply.
+class CopyPool {
+ public:
+  static CopyPool& get() { static CopyPool pool; return pool; }
+  // dst[0..n) = src[0..n), split over the pool and the calling thread; returns when done
+  // `pinned_side`: which of the two buffers the GPU's DMA engine touches next (0: dst, 1: src), see copy_and_demote
+  void copy(uint8_t* dst, const uint8_t* src, size_t n, int pinned_side) {
+    const size_t kMin = (size_t)512 << 10;  // not worth a hand-over below this
+    const int parts = (int)std::min<size_t>(workers_.size() + 1, (n + kMin - 1) / kMin);
+    if (parts <= 1) { copy_and_demote(dst, src, n, pinned_side); return; }
+    const size_t chunk = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      for (int i = 1; i < parts; ++i) {
+        const size_t off = chunk * i;
+        if (off >= n) break;
+        jobs_.push_back({dst + off, src + off, std::min(chunk, n - off), pinned_side});
+        ++pending_;
+      }
+    }
+    cv_.notify_all();
+    copy_and_demote(dst, src, std::min(chunk, n), pinned_side);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  struct Job { uint8_t* d; const uint8_t* s; size_t n; int pinned_side; };
+  CopyPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = hw >= 16 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+    if (const char* v = getenv("RIP_B200_COPY_THREADS")) n = std::max(0, atoi(v) - 1);
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_.notify_all();
+    for (std::thread& t : workers_) t.join();
+  }
+  void run() {
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+        if (stop_ && jobs_.empty()) return;
+        j = jobs_.front(); jobs_.pop_front();
+      }
+      copy_and_demote(j.d, j.s, j.n, j.pinned_side);
+      { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::deque<Job> jobs_;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
 }  // namespace
 
 struct rip_pipeline {
@@ -81,6 +169,8 @@ struct rip_pipeline {
   bool force_gather_remap = false;  // "debug/force_gather_remap": undistortion gathers from global memory even where the tile kernel applies
   std::vector<Span> spans;
   cudaError_t span_begin(int kind, cudaStream_t s) {
+    static const char* const kNames[SPAN_KINDS] = {"rip:pca_stats", "rip:wb_lut", "rip:fused_chain", "rip:undistort"};
+    nvtxRangePushA(kNames[kind]);  // NVTX range around the launch (tracing)
     if (!profile) return cudaSuccess;
     Span sp{kind, nullptr, nullptr};
     cudaError_t e = cudaEventCreate(&sp.a);
@@ -90,6 +180,7 @@ struct rip_pipeline {
     return e;
   }
   cudaError_t span_end(cudaStream_t s) {
+    nvtxRangePop();
     if (!profile || spans.empty()) return cudaSuccess;
     return cudaEventRecord(spans.back().b, s);
   }
@@ -116,6 +207,25 @@ struct rip_pipeline {
   uint8_t* h_stage_in = nullptr; size_t h_stage_in_cap = 0;
   uint8_t* h_stage_out = nullptr; size_t h_stage_out_cap = 0;
   cudaGraphExec_t graph_exec = nullptr;
+  // what the captured graph is valid for: frame shape / encoding, configuration, and the buffers baked into its nodes
+  struct GraphKey {
+    int rows = 0, cols = 0, channels = 0; std::string encoding; uint64_t epoch = 0;
+    const void *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr, *wb = nullptr, *color = nullptr, *stats = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return rows == o.rows && cols == o.cols && channels == o.channels && encoding == o.encoding && epoch == o.epoch && d_in == o.d_in &&
+             d_out == o.d_out && h_in == o.h_in && h_out == o.h_out && wb == o.wb && color == o.color && stats == o.stats;
+    }
+  } graph_key;
+  int graph_kernel_nodes = 0;  // kernels one replay launches (for stats/kernel_launches)
+  // the scratch buffers process_device uses are part of the key: a reallocation invalidates the graph
+  void remember_graph_buffers() { graph_key.wb = scratch.wb.ptr; graph_key.color = scratch.color.ptr; graph_key.stats = scratch.stats.ptr; }
+  GraphKey graph_key_partial() const { GraphKey k = graph_key; k.wb = k.color = k.stats = nullptr; return k; }
+  GraphKey graph_key_full() const { GraphKey k = graph_key_partial(); return (graph_key.wb == scratch.wb.ptr && graph_key.color == scratch.color.ptr && graph_key.stats == scratch.stats.ptr) ? k : GraphKey(); }
+  int graph_warm = 0;          // direct (un-captured) runs with the current key: lazy one-time initialisation happens there
+  bool use_graph = true;       // "apply/cuda_graph"
+  uint64_t config_epoch = 1;   // bumped by every setter / loader
+  long long graph_replays = 0;
+  double apply_us[5] = {0, 0, 0, 0, 0};  // last rip_apply: copy-in, enqueue (launch), wait for the device, copy-out ("stats/apply_us")
   // rip_apply_batch_device: one scratch set per caller stream, so that calls in flight on different streams never share
   // white-balance tables / statistics / intermediates (calls on ONE stream are ordered by the stream itself)
   std::map<cudaStream_t, Scratch> dev_scratch;
@@ -247,10 +357,10 @@ int ensure_tables(rip_pipeline* p) {
   RIP_CUDA(p, cudaDeviceSynchronize());  // nothing in flight may still read the old tables
   RIP_CUDA(p, p->d_tables.reserve(TABLE_BYTES));
   RIP_CUDA(p, cudaMemcpy(p->d_tables.ptr, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice));
-  std::vector<uint8_t> sblob(STRIP_TABLE_BYTES, 0);
+  std::vector<uint8_t> sblob(STRIP_BLOB_BYTES, 0);
   build_strip_blob(blob.data(), sblob.data());
-  RIP_CUDA(p, p->d_strip_tables.reserve(STRIP_TABLE_BYTES));
-  RIP_CUDA(p, cudaMemcpy(p->d_strip_tables.ptr, sblob.data(), STRIP_TABLE_BYTES, cudaMemcpyHostToDevice));
+  RIP_CUDA(p, p->d_strip_tables.reserve(STRIP_BLOB_BYTES));
+  RIP_CUDA(p, cudaMemcpy(p->d_strip_tables.ptr, sblob.data(), STRIP_BLOB_BYTES, cudaMemcpyHostToDevice));
   p->tables_valid = true; p->tables_key = key;
   return RIP_OK;
 }
@@ -349,9 +459,13 @@ int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
 // The pipeline proper, on device memory (raw_image_pipeline.hpp:143-172).
 // `keep_bgr_color`: the caller may later ask for getDistColorImage(), so the pre-undistortion image must exist as BGR8;
 // otherwise (batch entry points without a dist_color buffer) it is kept in the 4-byte format the gather prefers.
+// `no_undistort`: stop after the colour chain (the image getDistColorImage() returns); `reuse_wb`: the white-balance tables
+// in `sc` are those of this very frame (left there by the pass that produced the rectified image) -- do not recompute them
+// (the CCC Kalman tracker must not advance twice for one frame).
 int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8_t* d_in, size_t in_pitch,
                    size_t in_frame_stride, int n, uint8_t* d_out, size_t out_frame_stride, uint8_t* d_color_user,
-                   uint32_t stages_override, bool use_override, cudaStream_t stream, bool keep_bgr_color = true) {
+                   uint32_t stages_override, bool use_override, cudaStream_t stream, bool keep_bgr_color = true,
+                   bool no_undistort = false, bool reuse_wb = false) {
   const Params& q = p->hs.p;
   uint32_t stages = 0;
   int wb_kind = 0;
@@ -360,7 +474,7 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     int rc = stage_mask(p, g, stages, wb_kind);
     if (rc != RIP_OK) return rc;
   }
-  const bool undistort = g.undistort && !use_override;
+  const bool undistort = g.undistort && !use_override && !no_undistort;
   int launches = 0;
   if (stages & (ST_GAMMA | ST_VIG | ST_ENH)) { int rc = ensure_tables(p); if (rc != RIP_OK) return rc; }
   if (stages & ST_VIG) { int rc = ensure_vignetting(p, g.rows, g.cols, g.angle); if (rc != RIP_OK) return rc; }
@@ -394,7 +508,9 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
     RIP_CUDA(p, sc.wb.reserve((size_t)n * 768 * sizeof(float)));
     fp.wbf = sc.wb.as<float>();
     fp.k.wb_g_identity = wb_kind == 1 ? 1 : 0;  // pca leaves G untouched (white_balance.cpp:117-127)
-    if (wb_kind == 1) {
+    if (reuse_wb) {
+      // tables of this frame are already in sc.wb
+    } else if (wb_kind == 1) {
       RIP_CUDA(p, sc.stats.reserve((size_t)n * 8 * sizeof(unsigned long long)));
       RIP_CUDA(p, sc.coeff.reserve((size_t)n * 4 * sizeof(float)));
       fp.stats = sc.stats.as<unsigned long long>();
@@ -531,11 +647,12 @@ void rip_destroy(rip_pipeline* p) {
 
 const char* rip_last_error(const rip_pipeline* p) { return p ? p->last_error.c_str() : g_create_error.c_str(); }
 
-int rip_load_params(rip_pipeline* p, const char* path) { p->hs.load_params(path ? path : ""); return RIP_OK; }
-int rip_load_camera_calibration(rip_pipeline* p, const char* path) { p->hs.load_camera_calibration(path ? path : ""); return RIP_OK; }
-int rip_load_color_calibration(rip_pipeline* p, const char* path) { p->hs.load_color_calibration(path ? path : ""); return RIP_OK; }
-int rip_init_undistortion(rip_pipeline* p) { p->hs.init_undistortion(); return RIP_OK; }
+int rip_load_params(rip_pipeline* p, const char* path) { ++p->config_epoch; p->hs.load_params(path ? path : ""); return RIP_OK; }
+int rip_load_camera_calibration(rip_pipeline* p, const char* path) { ++p->config_epoch; p->hs.load_camera_calibration(path ? path : ""); return RIP_OK; }
+int rip_load_color_calibration(rip_pipeline* p, const char* path) { ++p->config_epoch; p->hs.load_color_calibration(path ? path : ""); return RIP_OK; }
+int rip_init_undistortion(rip_pipeline* p) { ++p->config_epoch; p->hs.init_undistortion(); return RIP_OK; }
 int rip_reset_white_balance_temporal_consistency(rip_pipeline* p) {
+  ++p->config_epoch;
   if (p->hs.p.wb_method == "ccc") p->ccc.pending_reset = true;  // white_balance.cpp:42-47 -> first_frame_ = true
   return RIP_OK;
 }
@@ -543,6 +660,7 @@ int rip_reset_white_balance_temporal_consistency(rip_pipeline* p) {
 // ---- setters --------------------------------------------------------------------------------
 int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   Params& q = p->hs.p;
+  ++p->config_epoch;  // a captured rip_apply graph is tied to the configuration it was captured under
   const bool v = value != 0;
   if (key_is(key, "gpu")) q.use_gpu = v;
   else if (key_is(key, "debug")) q.debug = v;
@@ -551,6 +669,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "debug/force_float_map")) p->force_float_map = v;
   else if (key_is(key, "debug/force_gather_remap")) p->force_gather_remap = v;
   else if (key_is(key, "undistortion/rect_mask")) p->emit_rect_mask = v;
+  else if (key_is(key, "apply/cuda_graph")) p->use_graph = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;
@@ -565,6 +684,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
 }
 
 int rip_set_int(rip_pipeline* p, const char* key, int value) {
+  ++p->config_epoch;  // a captured rip_apply graph is tied to the configuration it was captured under
   if (key_is(key, "flip/angle")) p->hs.p.flip_angle = value;
   else if (key_is(key, "debug/fused_kernel")) p->fused_kernel = value;
   else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown int key: ") + key);
@@ -573,6 +693,7 @@ int rip_set_int(rip_pipeline* p, const char* key, int value) {
 
 int rip_set_double(rip_pipeline* p, const char* key, double value) {
   Params& q = p->hs.p;
+  ++p->config_epoch;  // a captured rip_apply graph is tied to the configuration it was captured under
   if (key_is(key, "white_balance/clipping_percentile")) q.wb_clipping_percentile = value;
   else if (key_is(key, "gamma_correction/k")) q.gamma_k = value;
   else if (key_is(key, "color_enhancer/hue_gain")) p->hs.set_hue_gain(value);
@@ -586,6 +707,7 @@ int rip_set_double(rip_pipeline* p, const char* key, double value) {
 
 int rip_set_string(rip_pipeline* p, const char* key, const char* value) {
   Params& q = p->hs.p;
+  ++p->config_epoch;  // a captured rip_apply graph is tied to the configuration it was captured under
   const std::string v = value ? value : "";
   if (key_is(key, "debayer/encoding")) q.debayer_encoding = v;
   else if (key_is(key, "white_balance/method")) q.wb_method = v;
@@ -597,6 +719,7 @@ int rip_set_string(rip_pipeline* p, const char* key, const char* value) {
 
 int rip_set_doubles(rip_pipeline* p, const char* key, const double* v, int n) {
   Params& q = p->hs.p;
+  ++p->config_epoch;  // a captured rip_apply graph is tied to the configuration it was captured under
   auto need = [&](int want) -> int {
     if (n < want || !v)
       return p->fail(RIP_ERR_INVALID_ARGUMENT, std::string(key) + " needs " + std::to_string(want) + " values, got " + std::to_string(n));
@@ -658,6 +781,7 @@ int rip_get_int(rip_pipeline* p, const char* key, int* value) {
   else if (key_is(key, "rect/image_height")) *value = q.rect_h;
   else if (key_is(key, "rect/image_width")) *value = q.rect_w;
   else if (key_is(key, "stats/kernel_launches")) *value = (int)p->kernel_launches;
+  else if (key_is(key, "stats/graph_replays")) *value = (int)p->graph_replays;
   else if (key_is(key, "stats/ccc_u")) *value = p->ccc.uv_x;
   else if (key_is(key, "stats/ccc_v")) *value = p->ccc.uv_y;
   else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown int key: ") + key);
@@ -725,6 +849,7 @@ int rip_get_doubles(rip_pipeline* p, const char* key, double* values, int capaci
     }
     p->spans.clear();
   }
+  else if (key_is(key, "stats/apply_us")) { v.assign(p->apply_us, p->apply_us + 5); }
   else if (key_is(key, "stats/ccc_gains")) { int rc = ccc_fetch_pending(p); if (rc != RIP_OK) return rc; v = {(double)p->ccc.gain_b, (double)p->ccc.gain_g, (double)p->ccc.gain_r}; }
   else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown doubles key: ") + key);
   if (n) *n = (int)v.size();
@@ -790,6 +915,22 @@ int rip_output_shape(rip_pipeline* p, int rows, int cols, int channels, const ch
   return RIP_OK;
 }
 
+namespace {
+cudaError_t reserve_pinned(uint8_t*& ptr, size_t& cap, size_t n) {
+  if (n <= cap) return cudaSuccess;
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr; cap = 0;
+  cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&ptr), n);
+  if (e == cudaSuccess) cap = n;
+  return e;
+}
+}  // namespace
+
+// RawImagePipeline::apply (raw_image_pipeline.cpp:190-205).  One frame, host to host: the caller's image is copied into a
+// pinned staging buffer by a few host threads (CopyPool), the H2D copy, the kernels of the chain (4-byte intermediate +
+// TMA-staged tile undistortion, like the batch entry points) and the D2H copy run as ONE CUDA-graph launch from the second
+// frame of a (shape, configuration) on, and the result is copied out of pinned memory the same way.  The pre-undistortion
+// colour image is no longer produced on the way: getDistColorImage() recomputes it on demand from the retained input.
 int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int channels, size_t step, char* encoding,
               size_t encoding_capacity, uint8_t* out, size_t out_capacity, int* out_rows, int* out_cols, int* out_channels) {
   if (!data || !out || !encoding) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument");
@@ -804,17 +945,72 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
   const size_t row_bytes = (size_t)cols * channels;
   const size_t pitch = (row_bytes + 15) & ~(size_t)15;
+  if (!step) step = row_bytes;
   RIP_CUDA(p, p->d_in.reserve(pitch * rows));
   RIP_CUDA(p, p->d_out.reserve(out_bytes));
-  RIP_CUDA(p, cudaMemcpy2DAsync(p->d_in.ptr, pitch, data, step ? step : row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, p->stream));
-  rc = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * rows, 1, p->d_out.as<uint8_t>(), out_bytes, nullptr, 0,
-                      false, p->stream);
-  if (rc != RIP_OK) return rc;
-  RIP_CUDA(p, cudaMemcpyAsync(out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+  RIP_CUDA(p, reserve_pinned(p->h_stage_in, p->h_stage_in_cap, pitch * rows));
+  RIP_CUDA(p, reserve_pinned(p->h_stage_out, p->h_stage_out_cap, out_bytes));
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now_us();
+  // caller's image -> pinned staging (rows re-pitched to a multiple of 16 bytes: the TMA fast path)
+  if (step == pitch) CopyPool::get().copy(p->h_stage_in, data, pitch * rows, /*pinned_side=*/0);
+  else { for (int y = 0; y < rows; ++y) memcpy(p->h_stage_in + (size_t)y * pitch, data + (size_t)y * step, row_bytes); demote_range(p->h_stage_in, pitch * rows); }
+
+  auto enqueue = [&]() -> int {  // everything between the two host copies, on p->stream
+    RIP_CUDA(p, cudaMemcpyAsync(p->d_in.ptr, p->h_stage_in, pitch * rows, cudaMemcpyHostToDevice, p->stream));
+    int r = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * rows, 1, p->d_out.as<uint8_t>(), out_bytes, nullptr, 0,
+                           false, p->stream, /*keep_bgr_color=*/false);
+    if (r != RIP_OK) return r;
+    RIP_CUDA(p, cudaMemcpyAsync(p->h_stage_out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+    return RIP_OK;
+  };
+  // CCC keeps host-side state per frame (tracker reset flag, result pointers), profiling records events: both stay un-captured
+  const bool graph_ok = p->use_graph && !p->profile && wbk != 2;
+  rip_pipeline::GraphKey key;
+  key.rows = rows; key.cols = cols; key.channels = channels; key.encoding = encoding; key.epoch = p->config_epoch;
+  key.d_in = p->d_in.ptr; key.d_out = p->d_out.ptr; key.h_in = p->h_stage_in; key.h_out = p->h_stage_out;
+  bool launched = false;
+  const double t1 = now_us();
+  if (graph_ok && p->graph_exec && key == p->graph_key_full()) {
+    RIP_CUDA(p, cudaGraphLaunch(p->graph_exec, p->stream));
+    p->kernel_launches += p->graph_kernel_nodes; ++p->graph_replays;
+    launched = true;
+  }
+  if (!launched) {
+    const bool same = graph_ok && key == p->graph_key_partial();
+    if (same && p->graph_warm >= 1) {  // second frame of this (shape, configuration): every lazy initialisation has happened
+      if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+      const long long launches_before = p->kernel_launches;
+      cudaGraph_t graph = nullptr;
+      RIP_CUDA(p, cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue();
+      cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+      if (rc != RIP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      RIP_CUDA(p, ce);
+      ce = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      RIP_CUDA(p, ce);
+      p->graph_kernel_nodes = (int)(p->kernel_launches - launches_before);
+      p->graph_key = key; p->remember_graph_buffers();
+      RIP_CUDA(p, cudaGraphLaunch(p->graph_exec, p->stream));
+      ++p->graph_replays;
+    } else {
+      if ((rc = enqueue()) != RIP_OK) return rc;
+      if (same) ++p->graph_warm;
+      else { p->graph_key = key; p->remember_graph_buffers(); p->graph_warm = graph_ok ? 1 : 0;
+             if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; } }
+    }
+  }
+  const double t1b = now_us();
   if (wbk == 1) RIP_CUDA(p, cudaMemcpyAsync(p->last_pca, p->scratch.coeff.ptr, sizeof p->last_pca, cudaMemcpyDeviceToHost, p->stream));
   if (wbk == 2 && (rc = ccc_fetch_last(p->ccc, p->scratch.gains, p->stream, p->last_error)) != RIP_OK) return rc;
   p->ccc_pending_gains = nullptr;
+  const double t2 = now_us();
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
+  const double t3 = now_us();
+  CopyPool::get().copy(out, p->h_stage_out, out_bytes, /*pinned_side=*/1);
+  const double t4 = now_us();
+  p->apply_us[0] = t1 - t0; p->apply_us[1] = t1b - t1; p->apply_us[2] = t2 - t1b; p->apply_us[3] = t3 - t2; p->apply_us[4] = t4 - t3;
   p->have_frame = true; p->last_geom = g; p->last_in_encoding = encoding;
   memcpy(encoding, g.out_encoding.c_str(), g.out_encoding.size() + 1);
   if (out_rows) *out_rows = g.orows;
@@ -848,7 +1044,19 @@ int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity,
   int r = 0, c = 0;
   if (which == RIP_IMAGE_PROCESSED) { src = p->d_out.as<uint8_t>(); r = g.orows; c = g.ocols; }
   else if (which == RIP_IMAGE_DIST_COLOR) {
-    src = g.undistort ? p->scratch.color.as<uint8_t>() : p->d_out.as<uint8_t>(); r = g.frows; c = g.fcols;
+    r = g.frows; c = g.fcols;
+    if (!g.undistort) src = p->d_out.as<uint8_t>();
+    else {
+      // UndistortionModule's snapshot of its input (undistortion.hpp:68-71): recomputed on demand from the retained input
+      // with the white-balance tables the frame was processed with (apply() keeps it only in the 4-byte intermediate)
+      const size_t bytes = (size_t)r * c * g.ochannels;
+      RIP_CUDA(p, p->d_tmp.reserve(bytes));
+      const size_t pitch = (((size_t)g.cols * g.channels) + 15) & ~(size_t)15;
+      rc = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * g.rows, 1, p->d_tmp.as<uint8_t>(), bytes, nullptr, 0, false,
+                          p->stream, /*keep_bgr_color=*/true, /*no_undistort=*/true, /*reuse_wb=*/true);
+      if (rc != RIP_OK) return rc;
+      src = p->d_tmp.as<uint8_t>();
+    }
   } else if (which == RIP_IMAGE_DIST_DEBAYERED) {
     // FlipModule's snapshot (flip.hpp:36-45): recomputed on demand from the retained input
     r = g.frows; c = g.fcols;
@@ -932,6 +1140,43 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
     if ((rc = ccc_fetch_last(p->ccc, s.scratch.gains, s.stream, p->last_error)) != RIP_OK) return rc;
     p->ccc_pending_gains = nullptr;
   }
+  return RIP_OK;
+}
+
+int rip_apply_batch_host_multi(rip_pipeline* const* handles, int n_handles, const uint8_t* in, size_t in_frame_stride, int n_frames,
+                               int rows, int cols, int channels, const char* encoding, uint8_t* out, size_t out_frame_stride) {
+  if (!handles || n_handles <= 0 || !handles[0]) return RIP_ERR_INVALID_ARGUMENT;
+  rip_pipeline* p0 = handles[0];
+  if (!in || !out || n_frames <= 0) return p0->fail(RIP_ERR_INVALID_ARGUMENT, "null argument or empty batch");
+  for (int i = 0; i < n_handles; ++i) {
+    if (!handles[i]) return p0->fail(RIP_ERR_INVALID_ARGUMENT, "null pipeline handle");
+    const Params& q = handles[i]->hs.p;
+    if (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency && n_handles > 1)
+      return p0->fail(RIP_ERR_INVALID_ARGUMENT, "CCC temporal consistency tracks one camera stream: its frames cannot be sharded over pipelines");
+  }
+  FrameGeom g;
+  int rc = frame_geometry(p0, rows, cols, channels, encoding ? encoding : "", g);
+  if (rc != RIP_OK) return rc;
+  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
+  if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p0->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
+  // contiguous chunks, sizes differing by at most one (raw_image_pipeline_b200/sharding.py shard_range)
+  const int base = n_frames / n_handles, extra = n_frames % n_handles;
+  std::vector<int> status(n_handles, RIP_OK);
+  std::vector<std::thread> workers;
+  for (int i = 0; i < n_handles; ++i) {
+    const int begin = i * base + (i < extra ? i : extra), count = base + (i < extra ? 1 : 0);
+    if (count == 0) continue;
+    workers.emplace_back([=, &status] {
+      status[i] = rip_apply_batch_host(handles[i], in + (size_t)begin * in_frame_stride, in_frame_stride, count, rows, cols, channels,
+                                       encoding, out + (size_t)begin * out_frame_stride, out_frame_stride);
+    });
+  }
+  for (std::thread& t : workers) t.join();
+  for (int i = 0; i < n_handles; ++i)
+    if (status[i] != RIP_OK) {
+      if (i != 0) p0->last_error = "pipeline " + std::to_string(i) + ": " + handles[i]->last_error;
+      return status[i];
+    }
   return RIP_OK;
 }
 

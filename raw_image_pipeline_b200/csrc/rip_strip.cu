@@ -61,7 +61,6 @@ cudaError_t launch_fused_strip(uint32_t stages, bool wb_has_g_table, const Frame
   if (!bgrx) return launch_fused_strip_bgr8(key, p, g, im, om, om1, sm_count, stream);
   // experiment switch ("debug/fused_kernel" = 2 / 3): the benchmarked instantiation at 3 / 2 CTAs per SM (80 / 128 registers)
   if (variant == 3 && key == ST_ALL) return launch_strip_instance<ST_ALL, true, 3>(p, g, im, om, om1, sm_count, stream);
-  if (variant == 4 && key == ST_ALL) return launch_strip_instance<ST_ALL, true, 2>(p, g, im, om, om1, sm_count, stream);
   return dispatch_strip<0, true>(key, p, g, im, om, om1, sm_count, stream);
 }
 

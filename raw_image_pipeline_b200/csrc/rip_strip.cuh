@@ -16,9 +16,8 @@
 //   * the 4-byte intermediate (B,G,R,0 -- what the undistortion gather reads) leaves the registers directly: one
 //     16-byte store per lane and row, 512 contiguous bytes per warp.  BGR8 output (12 bytes per lane) is assembled in a
 //     per-warp staging buffer and written by the warp's own TMA stores, four rows at a time;
-//   * a CTA is 8 warps = 8 adjacent strips; CTA units (frame, row segment, strip group) are dealt round-robin over a
-//     persistent grid, so the grid works on a narrow band of one or two frames at a time (L2 locality of the vignetting
-//     mask and of the per-frame tables).
+//   * a CTA is 8 warps = 8 adjacent strips; every CTA of the persistent grid takes one contiguous run of the CTA units
+//     (frame, row segment, strip group), so it swaps the per-frame white-balance tables at most twice.
 //
 // Per-pixel arithmetic: chain_quad.cuh (bit-exact against pixel_math.cuh, which is bit-exact against the cv2 oracle).
 #pragma once
@@ -54,10 +53,10 @@ constexpr int GROUP_B = CH * OUT_ROW_B;
 // alignas() counts from the end of it), so the block is aligned at run time and the launch requests 4 KB of slack.
 template <uint32_t STAGES, bool BGRX>
 struct StripSmem {
-  // tables: a verbatim copy of the strip blob (chain_tables.hpp SOFF_*), truncated to what the stage set reads
-  static constexpr int TBL_RAW = (STAGES & ST_ENH) ? STRIP_TABLE_BYTES : (STAGES & ST_VIG) ? SOFF_SV : (STAGES & ST_GAMMA) ? SOFF_G2 : (STAGES & ST_WB) ? SOFF_GAMMA : 128;
+  // tables: the strip blob's layout (chain_tables.hpp SOFF_*), truncated to the prefix the stage set reads
+  static constexpr int TBL_RAW = ((STAGES & ST_CC) && (STAGES & ST_WB)) ? STRIP_TABLE_BYTES : (STAGES & ST_VIG) ? STRIP_VIG_END
+                                 : (STAGES & ST_ENH) ? STRIP_ENH_END : (STAGES & ST_WB) ? SOFF_SF : (STAGES & ST_GAMMA) ? SOFF_WB : 128;
   static constexpr int TBL = (TBL_RAW + 127) / 128 * 128;
-  static constexpr int COPY_LO = (STAGES & ST_VIG) ? 0 : SOFF_GAMMA;  // first blob byte a stage set without vignetting needs
   static constexpr int OFF_IN = TBL;                                   // [warp][slot][CHUNK_B]
   static constexpr int OFF_OUT = OFF_IN + NW * NS * CHUNK_B;           // [warp][buffer][row][384]
   static constexpr int OFF_MBAR = OFF_OUT + (BGRX ? 0 : NW * 2 * GROUP_B);
@@ -72,7 +71,13 @@ extern __shared__ uint8_t strip_smem_raw[];
 // (the G table holds the identity under pca, so the variant with a G lookup serves both white-balance methods)
 template <uint32_t STAGES>
 __device__ __noinline__ uint32_t chain_px_tail(uint32_t Bw, uint32_t Gw, uint32_t Rw, float m, const ChainConsts& k, const StripTables t) {
-  return chain_px<STAGES, 0, true, true, false>(Bw, Gw, Rw, m, k, t);
+  return chain_px<STAGES, 0, true, true>(Bw, Gw, Rw, m, k, t);
+}
+
+__device__ __forceinline__ void copy_table_range(uint8_t* sm, const uint8_t* blob, int lo, int hi, int tid) {
+  const uint4* src = reinterpret_cast<const uint4*>(blob);
+  uint4* dst = reinterpret_cast<uint4*>(sm);
+  for (int i = lo / 16 + tid; i < hi / 16; i += NT) dst[i] = __ldg(src + i);
 }
 
 // KEY = stage bits | KEY_WBG (the G channel has a white-balance table: ccc).  Colour calibration with a non-zero bias is
@@ -84,7 +89,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
                                                        const __grid_constant__ CUtensorMap out_map1) {
   constexpr uint32_t STAGES = KEY & ST_ALL;
   constexpr bool WBG = (KEY & KEY_WBG) != 0;
-  constexpr int UNR = (STAGES & (ST_VIG | ST_ENH)) ? 2 : 4;  // rows of straight-line code (the chain of 4 x 4 pixels would not fit the I-cache)
+  // rows of straight-line code: the whole chunk for the light stage sets; one row (rolled loop, CFA phase flipped per row)
+  // where the Lab / HSV chain of four pixels is already ~10 KB of code -- unrolled bodies thrash the instruction cache of
+  // warps that run out of step (measured: 7.2 vs 5.5 ms per 64 x 12 MP)
+  constexpr int UNR = (STAGES & (ST_VIG | ST_ENH)) ? 1 : 4;
   using L = StripSmem<STAGES, BGRX>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* const sm = strip_smem_raw + ((0u - smem_u32(strip_smem_raw)) & 4095u);  // 4096-byte aligned shared-window address
@@ -96,12 +104,9 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
     for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
     fence_mbar_init();
   }
-  if (STAGES & (ST_GAMMA | ST_VIG | ST_ENH)) {
-    constexpr int LO = L::COPY_LO / 16, HI = L::TBL_RAW / 16;
-    const uint4* src = reinterpret_cast<const uint4*>(P.strip_tables);
-    uint4* dst = reinterpret_cast<uint4*>(sm);
-    for (int i = LO + tid; i < HI; i += NT) dst[i] = __ldg(src + i);
-  }
+  if ((STAGES & ST_GAMMA) && !(STAGES & ST_VIG)) copy_table_range(sm, P.strip_tables, SOFF_GAMMA, SOFF_WB, tid);
+  if (STAGES & ST_ENH) copy_table_range(sm, P.strip_tables, SOFF_SF, STRIP_ENH_END, tid);
+  if (STAGES & ST_VIG) copy_table_range(sm, P.strip_tables, SOFF_LABC, STRIP_VIG_END, tid);
   __syncthreads();
   const StripTables T = strip_tables_at(taddr_of_shared(sm));
   const bool rev = P.angle == 180;
@@ -110,14 +115,26 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
   uint32_t slot = 0, ph = 0;  // this warp's ring: slot of the next chunk to consume, per-slot mbarrier parities
   uint32_t obuf = 0;          // BGR8 staging: group being filled
 
-  for (long long u = blockIdx.x; u < G.total_units; u += gridDim.x) {
+  // Unit list: frame-major, then row segment, then strip group.  With per-frame white-balance tables every CTA takes one
+  // contiguous run of it: it changes frame -- and reloads the tables behind two barriers -- at most twice (dealt
+  // round-robin, every unit of a CTA lies in a different frame: the reloads cost 28 % of the kernel).  Without them the
+  // units are dealt round-robin: the grid then works on one band of one frame at a time (measured 0.84 vs 0.88 ms).
+  constexpr bool PER_FRAME_TABLES = (STAGES & ST_WB) != 0;
+  const long long u_first = PER_FRAME_TABLES ? G.total_units * blockIdx.x / gridDim.x : (long long)blockIdx.x;
+  const long long u_end = PER_FRAME_TABLES ? G.total_units * (blockIdx.x + 1) / gridDim.x : G.total_units;
+  const long long u_step = PER_FRAME_TABLES ? 1 : (long long)gridDim.x;
+  for (long long u = u_first; u < u_end; u += u_step) {
     const int frame = (int)(u / G.units_per_frame);
     const int rem = (int)(u - (long long)frame * G.units_per_frame);
     const int seg = rem / G.ngroups, grp = rem - seg * G.ngroups;
-    if ((STAGES & ST_WB) && frame != cur_frame) {  // uniform over the CTA
-      __syncthreads();                             // nobody reads the previous frame's table any more
-      const float* src = P.wbf + (size_t)frame * 768;
-      for (int i = tid; i < 768; i += NT) sm[SOFF_WB + i] = (uint8_t)__float2int_rz(src[i]);  // plain load: written by a prior kernel
+    // per-frame white-balance tables (uniform over the CTA): floats where the colour calibration consumes them, bytes otherwise
+    if ((STAGES & ST_WB) && frame != cur_frame) {
+      __syncthreads();  // nobody reads the previous frame's tables any more
+      const float* src = P.wbf + (size_t)frame * 768;  // plain loads: written by a prior kernel
+      for (int i = tid; i < 768; i += NT) {
+        if (STAGES & ST_CC) reinterpret_cast<float*>(sm + SOFF_WBF)[i] = src[i];
+        else sm[SOFF_WB + i] = (uint8_t)__float2int_rz(src[i]);
+      }
       __syncthreads();
       cur_frame = frame;
     }
@@ -142,6 +159,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
     const bool tail_quad = (STAGES & ST_ENH) && oxb >= tail_start;
     const uint32_t colfix = x == 0 ? 0x3211u : (x + 4 == P.cols ? 0x2210u : 0x3210u);  // column 0 <- 1, W-1 <- W-2
     const BayerPhase phase = bayer_phase(ca, P.cfa);  // "even" rows: ca, ca + 2, ...
+    BayerPhaseRT phase_rt = bayer_phase_rt(ca, P.cfa);  // rolled row loop only: phase of the current centre row
 
     // chunk k of the unit holds Bayer rows ca - 3 + 4k .. ca + 4k: chunk 0 only supplies the two rows above the first
     // centre's bottom row, chunk k >= 1 the bottom rows of centres ca + 4(k-1) .. ca + 4(k-1) + 3
@@ -180,6 +198,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
     int ooff = oy0 * P.out_pitch + oxb * 4;       // BGRX only
     int voff = ye0 * P.vig_pitch + xc;            // mask in input-frame coordinates, floats
     const int lane_pos = 12 * (rev ? 31 - lane : lane);
+    const int sstep = rev ? -OUT_ROW_B : OUT_ROW_B;
     int done = 0;
 
     for (int k = 1; k <= nq; ++k) {
@@ -192,15 +211,23 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
         if (lane == 0) tma_wait_read<1>();  // the group about to be filled was handed to the TMA two groups ago
         __syncwarp();
         sp = sm_out + obuf * GROUP_B + (rev ? (CH - 1) * OUT_ROW_B : 0) + lane_pos;
+        asm volatile("" : "+l"(sp));  // keep the address in a register: recomputing it per row costs more than holding it
       }
-      // one output row: row `tt` = h * UNR + t of the chunk (t is a compile-time constant: the row's parity is t's)
-      auto row_step = [&](auto tc, int h) {
+      // one output row: row `tt` of the chunk.  `tc`: the row's parity when it is a compile-time constant (unrolled
+      // bodies), -1 when the phase is tracked at run time (rolled loop).
+      auto row_step = [&](auto tc, int tt) {
         constexpr int t = decltype(tc)::value;
-        const int tt = h * UNR + t;  // row of the chunk: centre row ca + 4(k-1) + tt, whose parity is t's
-        const BayerRow rs = load_bayer_row<(t & 1) == 0>(rowp + tt * ROW_W, phase);  // the bottom row has the other parity
         uint32_t Bw, Gw, Rw;
-        demosaic_window<(t & 1) != 0>(rn, rm, rs, phase, Bw, Gw, Rw);
-        rn = rm; rm = rs;
+        if constexpr (t < 0) {
+          const BayerRow rs = load_bayer_row_below(rowp + tt * ROW_W, phase_rt);
+          demosaic_window(rn, rm, rs, phase_rt, Bw, Gw, Rw);
+          phase_rt.flip();
+          rn = rm; rm = rs;
+        } else {
+          const BayerRow rs = load_bayer_row<(t & 1) == 0>(rowp + tt * ROW_W, phase);  // the bottom row has the other parity
+          demosaic_window<(t & 1) != 0>(rn, rm, rs, phase, Bw, Gw, Rw);
+          rn = rm; rm = rs;
+        }
         if (colfix != 0x3210u) { Bw = prmt(Bw, 0u, colfix); Gw = prmt(Gw, 0u, colfix); Rw = prmt(Rw, 0u, colfix); }
         float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         if (STAGES & ST_VIG) {
@@ -210,7 +237,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
         }
         uint32_t px[4];
         if (!tail_quad) {
-          chain_quad<STAGES, WBG, false>(Bw, Gw, Rw, m, P.k, T, px);
+          chain_quad<STAGES, WBG>(Bw, Gw, Rw, m, P.k, T, px);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) px[j] = chain_px_tail<STAGES>(Bw >> (8 * j), Gw >> (8 * j), Rw >> (8 * j), m[j], P.k, T);
@@ -223,18 +250,19 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
           ooff += ostep;
         } else {  // lanes beyond the frame edge write staging bytes the TMA store clips
           uint32_t* o = reinterpret_cast<uint32_t*>(sp);
-          if (rev) { o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542); sp -= OUT_ROW_B; }
-          else { o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542); sp += OUT_ROW_B; }
+          if (rev) { o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542); }
+          else { o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542); }
+          sp += sstep;
         }
       };
+      if constexpr (UNR == 1) {
 #pragma unroll 1
-      for (int h = 0; h < CH / UNR; ++h) {
-        row_step(std::integral_constant<int, 0>{}, h);
-        row_step(std::integral_constant<int, 1>{}, h);
-        if constexpr (UNR == 4) {
-          row_step(std::integral_constant<int, 2>{}, h);
-          row_step(std::integral_constant<int, 3>{}, h);
-        }
+        for (int tt = 0; tt < CH; ++tt) row_step(std::integral_constant<int, -1>{}, tt);
+      } else {
+        row_step(std::integral_constant<int, 0>{}, 0);
+        row_step(std::integral_constant<int, 1>{}, 1);
+        row_step(std::integral_constant<int, 2>{}, 2);
+        row_step(std::integral_constant<int, 3>{}, 3);
       }
       if (!BGRX) {  // hand the group to the TMA: one 4-row store, or row by row at the end of a ragged unit
         fence_async_smem();

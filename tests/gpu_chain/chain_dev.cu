@@ -21,9 +21,13 @@ __global__ void k_chain_dev(const __grid_constant__ DevArgs A) {
   uint8_t* const s_tab = dyn_raw + ((0u - (uint32_t)__cvta_generic_to_shared(dyn_raw)) & 4095u);
   __shared__ alignas(16) uint8_t s_blob[TABLE_BYTES];
   __shared__ float s_wbf[768];
-  for (int i = threadIdx.x; i < STRIP_TABLE_BYTES; i += blockDim.x) s_tab[i] = A.sblob[i];
+  for (int i = threadIdx.x; i < STRIP_BLOB_BYTES; i += blockDim.x) s_tab[i] = A.sblob[i];
   for (int i = threadIdx.x; i < TABLE_BYTES; i += blockDim.x) s_blob[i] = A.blob[i];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) { s_wbf[i] = A.wbf[i]; s_tab[SOFF_WB + i] = (uint8_t)__float2int_rz(A.wbf[i]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {  // per-frame tables, as k_fused_strip builds them
+    s_wbf[i] = A.wbf[i]; s_tab[SOFF_WB + i] = (uint8_t)__float2int_rz(A.wbf[i]);
+    reinterpret_cast<float*>(s_tab + SOFF_WBF)[i] = A.wbf[i];
+  }
   __syncthreads();
   const StripTables T = strip_tables_at(taddr_of_shared(s_tab));
   const ChainTables C = chain_tables_from_blob(s_blob, s_wbf);
@@ -35,8 +39,8 @@ __global__ void k_chain_dev(const __grid_constant__ DevArgs A) {
       m[j] = A.mask ? A.mask[i] : 1.0f;
     }
     uint32_t px[4];
-    if (A.wbg) chain_quad<STAGES, true, false>(Bw, Gw, Rw, m, A.k, T, px);
-    else chain_quad<STAGES, false, false>(Bw, Gw, Rw, m, A.k, T, px);
+    if (A.wbg) chain_quad<STAGES, true>(Bw, Gw, Rw, m, A.k, T, px);
+    else chain_quad<STAGES, false>(Bw, Gw, Rw, m, A.k, T, px);
     for (int j = 0; j < 4; ++j) {
       const long i = q * 4 + j;
       A.out_quad[3 * i] = px[j]; A.out_quad[3 * i + 1] = px[j] >> 8; A.out_quad[3 * i + 2] = px[j] >> 16;
@@ -63,7 +67,7 @@ extern "C" int chain_dev_run(unsigned stages, long n, const uint8_t* in, const f
                              const uint8_t* wb, const uint8_t* gamma, uint8_t* out_quad, uint8_t* out_ref) {
   ChainTableParams q;
   q.enh_gain[0] = enh[0]; q.enh_gain[1] = enh[1]; q.enh_gain[2] = enh[2];
-  std::vector<uint8_t> blob(TABLE_BYTES), sblob(STRIP_TABLE_BYTES);
+  std::vector<uint8_t> blob(TABLE_BYTES), sblob(STRIP_BLOB_BYTES);
   build_chain_blob(q, blob.data());
   if (stages & ST_GAMMA) {
     memcpy(blob.data() + OFF_GAMMA, gamma, 256);
@@ -80,11 +84,11 @@ extern "C" int chain_dev_run(unsigned stages, long n, const uint8_t* in, const f
   chain_consts_finish(a.k);
   uint8_t *d_in, *d_q, *d_r, *d_blob, *d_sblob; float *d_mask = nullptr, *d_wbf;
   if (cudaMalloc(&d_in, 3 * n) || cudaMalloc(&d_q, 3 * n) || cudaMalloc(&d_r, 3 * n) || cudaMalloc(&d_blob, TABLE_BYTES) ||
-      cudaMalloc(&d_sblob, STRIP_TABLE_BYTES) || cudaMalloc(&d_wbf, sizeof wbf)) return -1;
+      cudaMalloc(&d_sblob, STRIP_BLOB_BYTES) || cudaMalloc(&d_wbf, sizeof wbf)) return -1;
   if (mask) { if (cudaMalloc(&d_mask, 4 * n)) return -1; cudaMemcpy(d_mask, mask, 4 * n, cudaMemcpyHostToDevice); }
   cudaMemcpy(d_in, in, 3 * n, cudaMemcpyHostToDevice);
   cudaMemcpy(d_blob, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice);
-  cudaMemcpy(d_sblob, sblob.data(), STRIP_TABLE_BYTES, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_sblob, sblob.data(), STRIP_BLOB_BYTES, cudaMemcpyHostToDevice);
   cudaMemcpy(d_wbf, wbf, sizeof wbf, cudaMemcpyHostToDevice);
   a.in = d_in; a.mask = d_mask; a.out_quad = d_q; a.out_ref = d_r; a.blob = d_blob; a.sblob = d_sblob; a.wbf = d_wbf;
   int rc = run_stage<0>(stages & 31u, a);

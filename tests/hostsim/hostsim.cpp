@@ -100,16 +100,17 @@ void hs_chain(unsigned stages, long n, int width, const uint8_t* in, const float
 // `tail` != 0: every pixel is treated as a row-tail pixel of HSV2BGR (the strip kernel's out-of-line variant)
 void hs_chain_quad(unsigned stages, long n, int tail, const uint8_t* in, const float* mask, const float* cc, const float* bias,
                    const double* enh, const uint8_t* wb, const uint8_t* gamma, uint8_t* out) {
+  (void)bias;  // the strip kernel leaves configurations with a bias to the tile kernel
   const std::vector<uint8_t> blob = make_blob(enh, (stages & ST_GAMMA) ? gamma : nullptr);
-  std::vector<uint8_t> sblob(STRIP_TABLE_BYTES);
-  build_strip_blob(blob.data(), sblob.data());
+  std::vector<uint8_t> tab(STRIP_TABLE_BYTES);
+  build_strip_blob(blob.data(), tab.data());
   bool g_identity = true;
   for (int i = 0; i < 256; ++i) g_identity = g_identity && wb[256 + i] == i;
-  memcpy(sblob.data() + SOFF_WB, wb, 768);
-  const StripTables t = strip_tables_at(sblob.data());
+  memcpy(tab.data() + SOFF_WB, wb, 768);
+  for (int i = 0; i < 768; ++i) { const float f = (float)wb[i]; memcpy(tab.data() + SOFF_WBF + 4 * i, &f, 4); }  // as the kernel fills them
+  const StripTables t = strip_tables_at(tab.data());
   ChainConsts k;
-  memcpy(k.cc, cc, sizeof k.cc); memcpy(k.cc_bias, bias, sizeof k.cc_bias);
-  k.wb_g_identity = g_identity ? 1 : 0;
+  memcpy(k.cc, cc, sizeof k.cc); k.cc_bias[0] = k.cc_bias[1] = k.cc_bias[2] = 0.0f; k.wb_g_identity = g_identity ? 1 : 0;
   chain_consts_finish(k);
   for (long i = 0; i < n; i += 4) {
     uint32_t Bw = 0, Gw = 0, Rw = 0;
@@ -120,12 +121,11 @@ void hs_chain_quad(unsigned stages, long n, int tail, const uint8_t* in, const f
     }
     uint32_t px[4];
     switch (stages & ST_ALL) {
-    // the strip kernel's instantiations: no G table under pca (identity), no bias add when the bias is zero
+    // the strip kernel's instantiations: no G table under pca (identity)
 #define RIP_CASE(S) case S: \
-      if (tail) for (int q = 0; q < 4; ++q) px[q] = chain_px<S, 0, true, true, true>(Bw >> (8 * q), Gw >> (8 * q), Rw >> (8 * q), m[q], k, t); \
-      else if (g_identity && !k.has_bias) chain_quad<S, false, false>(Bw, Gw, Rw, m, k, t, px); \
-      else if (!k.has_bias) chain_quad<S, true, false>(Bw, Gw, Rw, m, k, t, px); \
-      else chain_quad<S, true, true>(Bw, Gw, Rw, m, k, t, px); \
+      if (tail) for (int q = 0; q < 4; ++q) px[q] = chain_px<S, 0, true, true>(Bw >> (8 * q), Gw >> (8 * q), Rw >> (8 * q), m[q], k, t); \
+      else if (g_identity) chain_quad<S, false>(Bw, Gw, Rw, m, k, t, px); \
+      else chain_quad<S, true>(Bw, Gw, Rw, m, k, t, px); \
       break;
       RIP_CASE(0) RIP_CASE(1) RIP_CASE(2) RIP_CASE(3) RIP_CASE(4) RIP_CASE(5) RIP_CASE(6) RIP_CASE(7)
       RIP_CASE(8) RIP_CASE(9) RIP_CASE(10) RIP_CASE(11) RIP_CASE(12) RIP_CASE(13) RIP_CASE(14) RIP_CASE(15)

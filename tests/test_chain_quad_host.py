@@ -54,7 +54,7 @@ def test_chain_quad_equals_chain_pixel_on_the_whole_cube(hostsim, stages):
     img = cube()
     rng = np.random.default_rng(100 + stages)
     kw = dict(mask=rng.uniform(1.0, 2.6, img.shape[:2]).astype(np.float32) if stages & 8 else None,
-              cc=CC_EXAMPLE if stages % 2 == 0 else CC2, bias=(0, 0, 0) if stages % 4 < 2 else (3.25, -7.5, 0.49),
+              cc=CC_EXAMPLE if stages % 4 < 2 else CC2, bias=(0, 0, 0),
               enh=(1.0, 1.2, 1.0) if stages % 3 else (1.1, 0.8, 1.3), wb=_wb_tables(rng, g_identity=(stages % 8) < 4),
               gamma=O.gamma_lut(0.8))
     ref = chain_ref(hostsim, stages, img, width=img.shape[1], **kw)   # width 4096: no row tail
