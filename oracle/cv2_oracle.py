@@ -103,6 +103,8 @@ def vignetting_mask(rows: int, cols: int, scale: float, a2: float, a4: float) ->
 class OracleParams:
     debayer_enabled: bool = True
     debayer_encoding: str = "auto"
+    # EXTENSION beyond the reference (which throws for 16-bit Bayer, debayer.cpp:76-78): accept bayer_*16, see debayer16()
+    debayer_allow_16bit: bool = False
     flip_enabled: bool = False
     flip_angle: int = 0
     wb_enabled: bool = False
@@ -160,6 +162,17 @@ def debayer(image: np.ndarray, encoding: str) -> Tuple[np.ndarray, str]:
     if encoding in BAYER_TYPES:
         raise ValueError("Encoding [" + encoding + "] is a valid pattern but is not supported!")
     return image, encoding
+
+
+def debayer16(image: np.ndarray, encoding: str) -> Tuple[np.ndarray, str]:
+    """EXTENSION (the reference lists the bayer_*16 names but throws for them).  Defined as what the
+    reference's own 8-bit code does, one depth up, followed by the 16 -> 8 bit reduction ROS' cv_bridge applies
+    (convertTo(CV_8U, 255 / 65535)): cv::demosaicing on the CV_16UC1 frame with the 8-bit path's code and R/B swap, then
+    saturate_cast<uchar>(v * (1 / 257.f)); the rest of the chain (cv::LUT, cvtColor ... all 8-bit only) runs on that."""
+    code = BAYER_CODES[encoding[:-2] + "8"]
+    out = cv2.demosaicing(image, code)
+    out = cv2.cvtColor(out, cv2.COLOR_RGB2BGR)
+    return cv2.convertScaleAbs(out, alpha=1.0 / 257.0), "bgr8"
 
 
 def flip(image: np.ndarray, angle: int) -> np.ndarray:
@@ -425,7 +438,10 @@ class OraclePipeline:
     def apply(self, image: np.ndarray, encoding: str, keep_stages: bool = False):
         p = self.p
         st = self.stages = {}
-        image, encoding = debayer(image, encoding)  # always runs (B-1)
+        if p.debayer_allow_16bit and encoding in ("bayer_rggb16", "bayer_bggr16", "bayer_gbrg16", "bayer_grbg16"):
+            image, encoding = debayer16(image, encoding)  # extension, see debayer16()
+        else:
+            image, encoding = debayer(image, encoding)  # always runs (B-1)
         if keep_stages: st["debayer"] = image
         if p.flip_enabled:
             image = flip(image, p.flip_angle)

@@ -38,6 +38,34 @@ RIP_HD void demosaic_at(const uint8_t* raw, int rows, int cols, size_t pitch, in
   }
 }
 
+// ---- EXTENSION: 16-bit Bayer (the reference throws for bayer_*16, debayer.cpp:76-78) -------------------
+// cv::demosaicing on a CV_16UC1 frame uses the same integer formulas and the same border rule one depth up; the result is
+// reduced to 8 bits like cv::Mat::convertTo(CV_8U, 1 / 257.f) == saturate_cast<uchar>(cvRound(v / 257.f)) -- which equals
+// (v + 128) / 257 for every 16-bit v (no ties: 257 is odd; checked over all 65536 values, tests/test_pixel_math_host.py).
+RIP_HD int reduce16to8(int v) { return (v + 128) / 257; }
+RIP_HD void demosaic_at16(const uint16_t* raw, int rows, int cols, size_t pitch_elems, int y, int x, int cfa, int& b, int& g, int& r) {
+  y = y < 1 ? 1 : (y > rows - 2 ? rows - 2 : y);
+  x = x < 1 ? 1 : (x > cols - 2 ? cols - 2 : x);
+  const uint16_t* p = raw + (size_t)y * pitch_elems + x;
+  const uint16_t* pn = p - pitch_elems;
+  const uint16_t* ps = p + pitch_elems;
+  const int c = p[0];
+  const bool row_has_r = ((y & 1) == ((cfa >> 1) & 1));
+  const bool col_is_r = ((x & 1) == (cfa & 1));
+  if (row_has_r == col_is_r) {
+    const int cross = (pn[0] + ps[0] + p[-1] + p[1] + 2) >> 2;
+    const int diag = (pn[-1] + pn[1] + ps[-1] + ps[1] + 2) >> 2;
+    g = cross;
+    if (row_has_r) { r = c; b = diag; } else { b = c; r = diag; }
+  } else {
+    const int horiz = (p[-1] + p[1] + 1) >> 1;
+    const int vert = (pn[0] + ps[0] + 1) >> 1;
+    g = c;
+    if (row_has_r) { r = horiz; b = vert; } else { b = horiz; r = vert; }
+  }
+  b = reduce16to8(b); g = reduce16to8(g); r = reduce16to8(r);
+}
+
 // ---- four horizontally adjacent sites x..x+3 (x % 4 == 0) from three rows of packed words --
 // w[row][0] = bytes x-4..x-1, w[row][1] = bytes x..x+3, w[row][2] = bytes x+4..x+7; rows are
 // y-1, y, y+1.  Valid only when all four sites are interior columns (1 <= x, x+3 <= W-2) and the

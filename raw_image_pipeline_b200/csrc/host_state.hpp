@@ -35,6 +35,7 @@ struct Params {
   // debayer.cpp / debayer.hpp
   bool debayer_enabled = true;
   std::string debayer_encoding = "auto";
+  bool debayer_allow_16bit = false;  // EXTENSION: accept bayer_*16 (the reference throws for them); "debayer/allow_16bit"
   // flip.cpp
   bool flip_enabled = false;
   int flip_angle = 0;

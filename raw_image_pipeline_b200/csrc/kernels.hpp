@@ -8,7 +8,7 @@
 
 namespace rip {
 
-enum : int { SRC_BAYER = 0, SRC_BGR = 1, SRC_RGB = 2, SRC_MONO = 3 };
+enum : int { SRC_BAYER = 0, SRC_BGR = 1, SRC_RGB = 2, SRC_MONO = 3, SRC_BAYER16 = 4 /* host side only: converted to SRC_BGR by launch_bayer16_to_bgr8 */ };
 
 struct FrameParams {
   const uint8_t* in;          // n_frames x rows x in_pitch
@@ -85,6 +85,10 @@ cudaError_t launch_fused_strip(uint32_t stages, bool wb_has_g_table, const Frame
 // have 3 channels: white_balance.hpp:50-52, color_calibration.hpp:47-49, color_enhancer.hpp:38-40)
 cudaError_t launch_mono(const FrameParams& p, bool gamma, cudaStream_t stream, int* launches);
 cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream, int* launches);
+// EXTENSION (16-bit Bayer, frame_math.cuh demosaic_at16): n frames of rows x cols u16 (`in_pitch` / `in_frame_stride` in
+// bytes) -> tightly packed BGR8 frames; the chain then runs on those like on a bgr8 input.
+cudaError_t launch_bayer16_to_bgr8(const uint8_t* in, long long in_frame_stride, int in_pitch, int rows, int cols, int n_frames, int cfa,
+                                   uint8_t* out, cudaStream_t stream, int* launches);
 // u8 validity mask of the rectified image: 255 where all four taps of the remap lie inside the rows x cols source
 cudaError_t launch_rect_mask(const float2* map, int orows, int ocols, int rows, int cols, uint8_t* mask, cudaStream_t stream, int* launches);
 // same remap from a 4-byte-per-pixel B,G,R,0 source (p.pitch = cols * 4) to BGR8

@@ -16,6 +16,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -40,12 +41,13 @@ thread_local std::string g_create_error;
 // per-stream scratch for one in-flight batch
 struct Scratch {
   DevBuf color;   // pre-undistortion images when the caller does not provide a buffer
+  DevBuf bgr8;    // 16-bit Bayer extension: the demosaiced frames reduced to BGR8
   DevBuf wb;      // n x 3 x 256 float
   DevBuf stats;   // n x 8 u64
   DevBuf coeff;   // n x 4 float (pca coefficients, kept for inspection)
   DevBuf gains;   // n x 3 float (ccc)
   DevBuf ccc;     // ccc working memory
-  void release() { color.release(); wb.release(); stats.release(); coeff.release(); gains.release(); ccc.release(); }
+  void release() { bgr8.release(); color.release(); wb.release(); stats.release(); coeff.release(); gains.release(); ccc.release(); }
 };
 
 struct Slot {  // host<->device streaming slot for rip_apply_batch_host
@@ -56,6 +58,7 @@ struct Slot {  // host<->device streaming slot for rip_apply_batch_host
 
 struct FrameGeom {
   int rows, cols, channels;  // input
+  int bytes_per_sample = 1;  // 2 for the 16-bit Bayer extension
   int src, cfa;              // SRC_*, CFA_*
   int angle;                 // effective flip angle
   int frows, fcols;          // after flip
@@ -291,6 +294,17 @@ int classify_encoding(rip_pipeline* p, const std::string& enc, int channels, int
     src = SRC_RGB;  // CPU branch swaps channels but keeps the encoding string (debayer.cpp:72-73)
     return RIP_OK;
   }
+  // EXTENSION (opt-in): 16-bit Bayer is demosaiced at 16 bits and reduced to 8 (frame_math.cuh demosaic_at16)
+  if (p->hs.p.debayer_allow_16bit) {
+    int c16 = -1;
+    if (enc == "bayer_rggb16") c16 = CFA_RGGB; else if (enc == "bayer_grbg16") c16 = CFA_GRBG;
+    else if (enc == "bayer_gbrg16") c16 = CFA_GBRG; else if (enc == "bayer_bggr16") c16 = CFA_BGGR;
+    if (c16 >= 0) {
+      if (channels != 1) return p->fail(RIP_ERR_INVALID_ARGUMENT, "Encoding [" + enc + "] needs a 1-channel image");
+      src = SRC_BAYER16; cfa = c16; out_enc = "bgr8";
+      return RIP_OK;
+    }
+  }
   // BAYER_TYPES with the reference's missing comma (debayer.hpp:77-78): these names throw
   static const char* kListed[] = {"bayer_rggb8bayer_bggr16", "bayer_gbrg16", "bayer_grbg16", "bayer_rggb16"};
   for (const char* s : kListed)
@@ -307,6 +321,7 @@ int frame_geometry(rip_pipeline* p, int rows, int cols, int channels, const std:
   int rc = classify_encoding(p, enc, channels, g.src, g.cfa, g.out_encoding);
   if (rc != RIP_OK) return rc;
   g.color = g.src != SRC_MONO;
+  g.bytes_per_sample = g.src == SRC_BAYER16 ? 2 : 1;
   g.angle = 0;
   if (q.flip_enabled && (q.flip_angle == 90 || q.flip_angle == 180 || q.flip_angle == 270)) g.angle = q.flip_angle;
   const bool swap = (g.angle == 90 || g.angle == 270);
@@ -484,6 +499,12 @@ int process_device(rip_pipeline* p, Scratch& sc, const FrameGeom& g, const uint8
   fp.in = d_in; fp.in_frame_stride = (long long)in_frame_stride; fp.in_pitch = (int)in_pitch;
   fp.rows = g.rows; fp.cols = g.cols; fp.orows = g.frows; fp.ocols = g.fcols; fp.n_frames = n;
   fp.cfa = g.cfa; fp.angle = g.angle; fp.src = g.src;
+  if (g.src == SRC_BAYER16) {  // extension: demosaic at 16 bits, reduce to BGR8, then the chain as for a bgr8 input
+    const size_t frame8 = (size_t)g.rows * g.cols * 3;
+    RIP_CUDA(p, sc.bgr8.reserve(frame8 * n));
+    RIP_CUDA(p, launch_bayer16_to_bgr8(d_in, (long long)in_frame_stride, (int)in_pitch, g.rows, g.cols, n, g.cfa, sc.bgr8.as<uint8_t>(), stream, &launches));
+    fp.in = sc.bgr8.as<uint8_t>(); fp.in_frame_stride = (long long)frame8; fp.in_pitch = g.cols * 3; fp.src = SRC_BGR;
+  }
   fp.tables = p->d_tables.as<uint8_t>();
   fp.strip_tables = p->d_strip_tables.as<uint8_t>();
   fp.vig = p->d_vig.as<float>(); fp.vig_pitch = p->vig_pitch;
@@ -671,6 +692,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "undistortion/rect_mask")) p->emit_rect_mask = v;
   else if (key_is(key, "apply/cuda_graph")) p->use_graph = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
+  else if (key_is(key, "debayer/allow_16bit")) q.debayer_allow_16bit = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
   else if (key_is(key, "white_balance/enabled")) q.wb_enabled = v;
   else if (key_is(key, "white_balance/temporal_consistency")) q.wb_temporal_consistency = v;
@@ -747,6 +769,7 @@ int rip_get_bool(rip_pipeline* p, const char* key, int* value) {
   if (key_is(key, "gpu")) v = q.use_gpu;
   else if (key_is(key, "debug")) v = q.debug;
   else if (key_is(key, "debayer/enabled")) v = q.debayer_enabled;
+  else if (key_is(key, "debayer/allow_16bit")) v = q.debayer_allow_16bit;
   else if (key_is(key, "flip/enabled")) v = q.flip_enabled;
   else if (key_is(key, "white_balance/enabled")) v = q.wb_enabled;
   else if (key_is(key, "white_balance/temporal_consistency")) v = q.wb_temporal_consistency;
@@ -943,7 +966,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   if (out_capacity < out_bytes) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "output buffer too small");
   if (g.out_encoding.size() + 1 > encoding_capacity) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "encoding buffer too small");
   if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
-  const size_t row_bytes = (size_t)cols * channels;
+  const size_t row_bytes = (size_t)cols * channels * g.bytes_per_sample;
   const size_t pitch = (row_bytes + 15) & ~(size_t)15;
   if (!step) step = row_bytes;
   RIP_CUDA(p, p->d_in.reserve(pitch * rows));
@@ -1051,7 +1074,7 @@ int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity,
       // with the white-balance tables the frame was processed with (apply() keeps it only in the 4-byte intermediate)
       const size_t bytes = (size_t)r * c * g.ochannels;
       RIP_CUDA(p, p->d_tmp.reserve(bytes));
-      const size_t pitch = (((size_t)g.cols * g.channels) + 15) & ~(size_t)15;
+      const size_t pitch = (((size_t)g.cols * g.channels * g.bytes_per_sample) + 15) & ~(size_t)15;
       rc = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * g.rows, 1, p->d_tmp.as<uint8_t>(), bytes, nullptr, 0, false,
                           p->stream, /*keep_bgr_color=*/true, /*no_undistort=*/true, /*reuse_wb=*/true);
       if (rc != RIP_OK) return rc;
@@ -1062,7 +1085,7 @@ int rip_get_image(rip_pipeline* p, int which, uint8_t* out, size_t out_capacity,
     r = g.frows; c = g.fcols;
     const size_t bytes = (size_t)r * c * g.ochannels;
     RIP_CUDA(p, p->d_tmp.reserve(bytes));
-    const size_t pitch = (((size_t)g.cols * g.channels) + 15) & ~(size_t)15;
+    const size_t pitch = (((size_t)g.cols * g.channels * g.bytes_per_sample) + 15) & ~(size_t)15;
     Scratch dummy;
     rc = process_device(p, dummy, g, p->d_in.as<uint8_t>(), pitch, pitch * g.rows, 1, p->d_tmp.as<uint8_t>(), bytes, nullptr, 0, true,
                         p->stream);
@@ -1085,7 +1108,7 @@ int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame
   int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
   if (rc != RIP_OK) return rc;
   if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
-  const size_t pitch = (size_t)cols * channels;
+  const size_t pitch = (size_t)cols * channels * g.bytes_per_sample;
   if (in_frame_stride < pitch * rows) return p->fail(RIP_ERR_INVALID_ARGUMENT, "in_frame_stride smaller than a frame");
   if (out_frame_stride < (size_t)g.orows * g.ocols * g.ochannels) return p->fail(RIP_ERR_INVALID_ARGUMENT, "out_frame_stride smaller than a frame");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -1096,19 +1119,16 @@ int rip_apply_batch_device(rip_pipeline* p, const uint8_t* d_in, size_t in_frame
   return rc;
 }
 
-int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames, int rows, int cols,
-                         int channels, const char* encoding, uint8_t* out, size_t out_frame_stride) {
-  if (!in || !out || n_frames <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument or empty batch");
-  FrameGeom g;
-  int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
-  if (rc != RIP_OK) return rc;
-  if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
-  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
-  if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
-  // chunk so that copies of chunk i+1 / i-1 overlap the kernels of chunk i
+}  // extern "C"
+
+// The body of the host batch entry points: frames are taken chunk by chunk from `next_chunk` (which returns the first frame
+// of the next chunk and its length, or a length of 0 when the batch is exhausted) and pushed through three slots so that the
+// copies of chunk i+1 / i-1 overlap the kernels of chunk i.
+template <class NextChunk>
+static int apply_host_chunks(rip_pipeline* p, const FrameGeom& g, const uint8_t* in, size_t in_frame_stride, int rows, int cols, int channels,
+                             uint8_t* out, size_t out_frame_stride, NextChunk next_chunk) {
+  const size_t in_frame = (size_t)rows * cols * channels * g.bytes_per_sample, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
   const int kSlots = 3;
-  int chunk = (int)((48u << 20) / (in_frame + out_frame));
-  chunk = chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
   if (p->slots.size() < (size_t)kSlots) {
     const size_t old = p->slots.size();
     p->slots.resize(kSlots);
@@ -1118,29 +1138,56 @@ int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_str
   // consistency on, all chunks go through one slot so that they execute in order on one CUDA stream.
   const Params& q = p->hs.p;
   const int n_slots = (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency) ? 1 : kSlots;
-  int slot_i = 0, last_slot = -1;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, slot_i = (slot_i + 1) % n_slots) {
-    last_slot = slot_i;
-    const int n = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+  int slot_i = 0, last_slot = -1, rc = RIP_OK;
+  for (;; slot_i = (slot_i + 1) % n_slots) {
     Slot& s = p->slots[slot_i];
-    RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again
+    RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again; only then is the next chunk claimed
+    int f0 = 0, n = 0;
+    next_chunk(&f0, &n);
+    if (n <= 0) break;
+    last_slot = slot_i;
     RIP_CUDA(p, s.in.reserve(in_frame * n));
     RIP_CUDA(p, s.out.reserve(out_frame * n));
     RIP_CUDA(p, cudaMemcpy2DAsync(s.in.ptr, in_frame, in + (size_t)f0 * in_frame_stride, in_frame_stride, in_frame, n,
                                   cudaMemcpyHostToDevice, s.stream));
-    rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels, in_frame, n, s.out.as<uint8_t>(), out_frame,
+    rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels * g.bytes_per_sample, in_frame, n, s.out.as<uint8_t>(), out_frame,
                         nullptr, 0, false, s.stream, /*keep_bgr_color=*/false);
     if (rc != RIP_OK) return rc;
     RIP_CUDA(p, cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_frame_stride, s.out.ptr, out_frame, out_frame, n,
                                   cudaMemcpyDeviceToHost, s.stream));
   }
   for (Slot& s : p->slots) RIP_CUDA(p, cudaStreamSynchronize(s.stream));
-  if (last_slot >= 0 && q.wb_enabled && q.wb_method == "ccc") {  // the estimate of the batch's last frame, like after apply()
+  if (last_slot >= 0 && q.wb_enabled && q.wb_method == "ccc") {  // the estimate of the last frame this pipeline saw, like after apply()
     Slot& s = p->slots[last_slot];
     if ((rc = ccc_fetch_last(p->ccc, s.scratch.gains, s.stream, p->last_error)) != RIP_OK) return rc;
     p->ccc_pending_gains = nullptr;
   }
   return RIP_OK;
+}
+
+static int host_chunk_frames(size_t in_frame, size_t out_frame) {
+  const int chunk = (int)((48u << 20) / (in_frame + out_frame));
+  return chunk < 1 ? 1 : (chunk > 16 ? 16 : chunk);
+}
+
+extern "C" {
+
+int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_frame_stride, int n_frames, int rows, int cols,
+                         int channels, const char* encoding, uint8_t* out, size_t out_frame_stride) {
+  if (!in || !out || n_frames <= 0) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument or empty batch");
+  FrameGeom g;
+  int rc = frame_geometry(p, rows, cols, channels, encoding ? encoding : "", g);
+  if (rc != RIP_OK) return rc;
+  if ((rc = ensure_cuda(p)) != RIP_OK) return rc;
+  const size_t in_frame = (size_t)rows * cols * channels * g.bytes_per_sample, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
+  if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
+  const int chunk = host_chunk_frames(in_frame, out_frame);
+  int next = 0;
+  return apply_host_chunks(p, g, in, in_frame_stride, rows, cols, channels, out, out_frame_stride, [&](int* f0, int* n) {
+    *f0 = next;
+    *n = (n_frames - next) < chunk ? (n_frames - next) : chunk;
+    next += *n;
+  });
 }
 
 int rip_apply_batch_host_multi(rip_pipeline* const* handles, int n_handles, const uint8_t* in, size_t in_frame_stride, int n_frames,
@@ -1154,23 +1201,35 @@ int rip_apply_batch_host_multi(rip_pipeline* const* handles, int n_handles, cons
     if (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency && n_handles > 1)
       return p0->fail(RIP_ERR_INVALID_ARGUMENT, "CCC temporal consistency tracks one camera stream: its frames cannot be sharded over pipelines");
   }
-  FrameGeom g;
-  int rc = frame_geometry(p0, rows, cols, channels, encoding ? encoding : "", g);
-  if (rc != RIP_OK) return rc;
-  const size_t in_frame = (size_t)rows * cols * channels, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
+  std::vector<FrameGeom> geom(n_handles);
+  for (int i = 0; i < n_handles; ++i) {
+    const int rc = frame_geometry(handles[i], rows, cols, channels, encoding ? encoding : "", geom[i]);
+    if (rc != RIP_OK) {
+      if (i != 0) p0->last_error = "pipeline " + std::to_string(i) + ": " + handles[i]->last_error;
+      return rc;
+    }
+  }
+  const FrameGeom& g = geom[0];
+  const size_t in_frame = (size_t)rows * cols * channels * g.bytes_per_sample, out_frame = (size_t)g.orows * g.ocols * g.ochannels;
   if (in_frame_stride < in_frame || out_frame_stride < out_frame) return p0->fail(RIP_ERR_INVALID_ARGUMENT, "frame stride smaller than a frame");
-  // contiguous chunks, sizes differing by at most one (raw_image_pipeline_b200/sharding.py shard_range)
-  const int base = n_frames / n_handles, extra = n_frames % n_handles;
+  // Frames are independent, so the chunks are dealt on demand rather than as fixed shards: the GPUs of one box do
+  // not see the same host bandwidth (profiles/pcie_ceiling.json: 7.4 against 15.9 GB/s per GPU with eight busy), and with
+  // fixed shards the whole batch waits for the slowest link.  A pipeline claims its next chunk when one of its three slots
+  // is free again.  Every frame gets the same bytes whichever pipeline takes it (all pipelines carry the same configuration).
+  const int chunk = host_chunk_frames(in_frame, out_frame);
+  std::atomic<int> next{0};
+  auto claim = [&](int* f0, int* n) {
+    const int b = next.fetch_add(chunk, std::memory_order_relaxed);
+    *f0 = b;
+    *n = b >= n_frames ? 0 : ((n_frames - b) < chunk ? (n_frames - b) : chunk);
+  };
   std::vector<int> status(n_handles, RIP_OK);
   std::vector<std::thread> workers;
-  for (int i = 0; i < n_handles; ++i) {
-    const int begin = i * base + (i < extra ? i : extra), count = base + (i < extra ? 1 : 0);
-    if (count == 0) continue;
-    workers.emplace_back([=, &status] {
-      status[i] = rip_apply_batch_host(handles[i], in + (size_t)begin * in_frame_stride, in_frame_stride, count, rows, cols, channels,
-                                       encoding, out + (size_t)begin * out_frame_stride, out_frame_stride);
+  for (int i = 0; i < n_handles; ++i)
+    workers.emplace_back([&, i] {
+      if ((status[i] = ensure_cuda(handles[i])) != RIP_OK) return;  // also makes the pipeline's device current on this thread
+      status[i] = apply_host_chunks(handles[i], geom[i], in, in_frame_stride, rows, cols, channels, out, out_frame_stride, claim);
     });
-  }
   for (std::thread& t : workers) t.join();
   for (int i = 0; i < n_handles; ++i)
     if (status[i] != RIP_OK) {

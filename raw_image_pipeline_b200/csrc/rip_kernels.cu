@@ -556,6 +556,33 @@ cudaError_t launch_remap(int channels, const RemapParams& p, cudaStream_t stream
   return cudaGetLastError();
 }
 
+// EXTENSION: 16-bit Bayer -> BGR8 (frame_math.cuh demosaic_at16).  One thread per pixel, three byte stores; a pre-pass, not
+// a tuned kernel -- the fast paths are for the 8-bit encodings the reference supports.
+__global__ void __launch_bounds__(256) k_bayer16_to_bgr8(const uint8_t* __restrict__ in, long long in_frame_stride, int in_pitch, int rows,
+                                                         int cols, int n_frames, int cfa, uint8_t* __restrict__ out) {
+  const long long per_frame = (long long)rows * cols, total = per_frame * n_frames;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / per_frame);
+    const long long rem = i - (long long)f * per_frame;
+    const int y = (int)(rem / cols), x = (int)(rem - (long long)y * cols);
+    int b, g, r;
+    demosaic_at16(reinterpret_cast<const uint16_t*>(in + (long long)f * in_frame_stride), rows, cols, (size_t)in_pitch >> 1, y, x, cfa, b, g, r);
+    uint8_t* o = out + 3 * i;
+    o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+  }
+}
+
+cudaError_t launch_bayer16_to_bgr8(const uint8_t* in, long long in_frame_stride, int in_pitch, int rows, int cols, int n_frames, int cfa,
+                                   uint8_t* out, cudaStream_t stream, int* launches) {
+  const long long total = (long long)rows * cols * n_frames;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (launches) ++*launches;
+  k_bayer16_to_bgr8<<<(int)blocks, 256, 0, stream>>>(in, in_frame_stride, in_pitch, rows, cols, n_frames, cfa, out);
+  return cudaGetLastError();
+}
+
 // Validity mask of the rectified image (the `rect_mask_` the reference declares but never fills, undistortion.hpp:136):
 // 255 where all four bilinear taps of cv::remap lie inside the source image -- the pixel is an interpolation of real
 // pixels only --, 0 where the constant border contributes.  Depends on the map and the source size only.

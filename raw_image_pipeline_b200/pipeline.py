@@ -30,6 +30,10 @@ def _raise(code: int, msg: str):
     raise RawImagePipelineError(code, msg)
 
 
+def _is_16bit(encoding: str) -> bool:
+    return encoding in ("bayer_rggb16", "bayer_bggr16", "bayer_gbrg16", "bayer_grbg16")
+
+
 class RawImagePipeline:
     def __init__(self, use_gpu: bool = False, params_path: Optional[str] = None, calibration_path: str = "",
                  color_calibration_path: str = "", device: Optional[int] = None):
@@ -105,9 +109,11 @@ class RawImagePipeline:
         return r.value, c.value, k.value
 
     def _run(self, image: np.ndarray, encoding: str) -> Tuple[np.ndarray, str]:
-        if image.dtype != np.uint8 or image.ndim not in (2, 3):
-            raise ValueError("image must be a uint8 array of shape (rows, cols) or (rows, cols, channels)")
-        img = image if image.strides[-1] == 1 and (image.ndim == 2 or image.strides[1] == image.shape[2]) \
+        want = np.uint16 if self._reads_16bit(encoding) else np.uint8
+        if image.dtype != want or image.ndim not in (2, 3):
+            raise ValueError(f"image must be a {np.dtype(want).name} array of shape (rows, cols) or (rows, cols, channels)")
+        item = image.dtype.itemsize
+        img = image if image.strides[-1] == item and (image.ndim == 2 or image.strides[1] == image.shape[2] * item) \
             else np.ascontiguousarray(image)
         rows, cols = img.shape[0], img.shape[1]
         ch = img.shape[2] if img.ndim == 3 else 1
@@ -138,8 +144,9 @@ class RawImagePipeline:
 
     def process_batch(self, frames: np.ndarray, encoding: str, out: Optional[np.ndarray] = None) -> np.ndarray:
         """n frames host -> host through rip_apply_batch_host (pinned memory gives full PCIe rate)."""
-        if frames.dtype != np.uint8 or frames.ndim not in (3, 4) or not frames.flags.c_contiguous:
-            raise ValueError("frames must be a C-contiguous uint8 array (n, rows, cols[, channels])")
+        want = np.uint16 if self._reads_16bit(encoding) else np.uint8
+        if frames.dtype != want or frames.ndim not in (3, 4) or not frames.flags.c_contiguous:
+            raise ValueError(f"frames must be a C-contiguous {np.dtype(want).name} array (n, rows, cols[, channels])")
         n, rows, cols = frames.shape[:3]
         ch = frames.shape[3] if frames.ndim == 4 else 1
         orows, ocols, och = self.output_shape(frames.shape[1:], encoding)
@@ -149,7 +156,8 @@ class RawImagePipeline:
               or out.size != n * orows * ocols * och):
             # the C entry point writes n tightly packed frames through the raw pointer: anything else corrupts memory
             raise ValueError(f"out must be a writable C-contiguous uint8 array of {n}x{orows}x{ocols}x{och} values")
-        self.process_batch_ptr(frames.ctypes.data, n, rows, cols, ch, encoding, out.ctypes.data, host=True)
+        self.process_batch_ptr(frames.ctypes.data, n, rows, cols, ch, encoding, out.ctypes.data, host=True,
+                               in_frame_stride=rows * cols * ch * frames.dtype.itemsize)
         return out
 
     def process_batch_ptr(self, in_ptr: int, n: int, rows: int, cols: int, channels: int, encoding: str, out_ptr: int,
@@ -157,9 +165,10 @@ class RawImagePipeline:
                           in_frame_stride: Optional[int] = None, out_frame_stride: Optional[int] = None):
         """Raw-pointer batch entry (device or host memory); see rip_apply_batch_device/_host."""
         orows, ocols, och = self.output_shape((rows, cols, channels), encoding)
-        ins = in_frame_stride if in_frame_stride is not None else rows * cols * channels
+        bps = 2 if self._reads_16bit(encoding) else 1
+        ins = in_frame_stride if in_frame_stride is not None else rows * cols * channels * bps
         outs = out_frame_stride if out_frame_stride is not None else orows * ocols * och
-        if n <= 0 or ins < rows * cols * channels or outs < orows * ocols * och:
+        if n <= 0 or ins < rows * cols * channels * bps or outs < orows * ocols * och:
             raise ValueError("process_batch_ptr: n must be positive and the frame strides at least one frame")
         if host:
             self._check(self._lib.rip_apply_batch_host(self._h, in_ptr, ins, n, rows, cols, channels, encoding.encode(),
@@ -181,6 +190,14 @@ class RawImagePipeline:
     def set_debug(self, debug): self._set_bool("debug", debug)
     def set_debayer(self, enabled): self._set_bool("debayer/enabled", enabled)
     def set_debayer_encoding(self, encoding): self._set_string("debayer/encoding", encoding)
+    def _reads_16bit(self, encoding: str) -> bool:
+        """16-bit samples are read only with the opt-in extension on; otherwise the 16-bit Bayer names throw the
+        reference's "valid pattern but is not supported" before any pixel is touched (debayer.cpp:76-78)."""
+        return _is_16bit(encoding) and self._get_bool("debayer/allow_16bit")
+
+    def set_debayer_allow_16bit(self, enabled):
+        """EXTENSION (not in the reference, which throws for bayer_*16): accept 16-bit Bayer frames (uint16 arrays)."""
+        self._set_bool("debayer/allow_16bit", enabled)
     def set_flip(self, enabled): self._set_bool("flip/enabled", enabled)
     def set_flip_angle(self, angle): self._set_int("flip/angle", angle)
     def set_white_balance(self, enabled): self._set_bool("white_balance/enabled", enabled)

@@ -173,6 +173,18 @@ void hs_demosaic(const uint8_t* raw, int rows, int cols, int cfa, int angle, int
     }
 }
 
+// 16-bit Bayer extension: demosaic at 16 bits + reduction to BGR8 (frame_math.cuh demosaic_at16)
+void hs_demosaic16(const uint16_t* raw, int rows, int cols, int cfa, uint8_t* out) {
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      int b, g, r;
+      demosaic_at16(raw, rows, cols, (size_t)cols, y, x, cfa, b, g, r);
+      uint8_t* o = out + ((size_t)y * cols + x) * 3;
+      o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+    }
+}
+int hs_reduce16to8(int v) { return reduce16to8(v); }
+
 void hs_remap(const uint8_t* src, int rows, int cols, int ch, const float* mx, const float* my, int orows, int ocols,
               uint8_t* out) {
   for (long i = 0; i < (long)orows * ocols; ++i) {

@@ -111,3 +111,28 @@ def test_multi_gpu_pipeline_shards_a_batch(oracle_built):
             assert_same(s_out[j], ref, f"stream {s_i} frame {j}")
             k += 1
     assert mp.kernel_launches() > 0
+
+
+@pytest.mark.parametrize("enc", ["bayer_rggb16", "bayer_bggr16"])
+@pytest.mark.parametrize("flip", [0, 90, 180])
+def test_16bit_bayer_extension(oracle_built, enc, flip):
+    """bayer_*16 (uint16 frames): rejected like the reference does unless set_debayer_allow_16bit(True); then demosaiced at
+    16 bits, reduced to 8 (oracle/cv2_oracle.py debayer16) and run through the full chain -- single frame and batch."""
+    rows, cols = 270, 368
+    rng = np.random.default_rng(77)
+    frames = (rng.integers(0, 4096, (3, rows, cols), dtype=np.uint16) << 4)   # 12-bit sensor data, MSB-aligned
+    frames[1] = rng.integers(0, 65536, (rows, cols), dtype=np.uint16)
+    kw = dict(FULL); kw["flip"] = flip
+    p, o = make_pair(rows, cols, **kw)
+    if enc != "bayer_bggr16":   # (the reference's name list has a typo for bggr16: that one falls through as an unknown encoding)
+        with pytest.raises(ValueError, match="valid pattern but is not supported"):
+            p.process(frames[0], enc)
+    p.set_debayer_allow_16bit(True)
+    o.p.debayer_allow_16bit = True
+    refs = [o.apply(frames[i], enc)[0] for i in range(3)]
+    for i in range(3):
+        assert_same(p.process(frames[i], enc), refs[i], f"{enc} flip {flip} frame {i}")
+    batch = p.process_batch(frames, enc)
+    for i in range(3):
+        assert_same(batch[i], refs[i], f"{enc} flip {flip} batch frame {i}")
+    assert p.output_shape((rows, cols), enc)[2] == 3

@@ -289,3 +289,27 @@ def test_gain_lut(hostsim, gain):
     x = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, axis=2)
     ref = cv2.multiply(x, (g, g, g, 0.0))
     assert np.array_equal(ref[0, :, 0], lut)
+
+
+# ---- 16-bit Bayer extension --------------------------------------------------------------------------
+def test_reduce16to8_equals_cv2_convert_for_every_value(hostsim):
+    v = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    ref = cv2.convertScaleAbs(v, alpha=1.0 / 257.0)   # == Mat::convertTo(CV_8U, 1 / 257.f)
+    hostsim.hs_reduce16to8.restype = ctypes.c_int
+    got = np.array([hostsim.hs_reduce16to8(int(x)) for x in range(0, 65536, 1)], np.uint8).reshape(256, 256)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("enc", ["bayer_rggb16", "bayer_grbg16", "bayer_gbrg16", "bayer_bggr16"])
+@pytest.mark.parametrize("shape", [(480, 640), (11, 13), (10, 12), (3, 3), (4, 9)])
+def test_demosaic16_against_cv2(hostsim, enc, shape):
+    rng = np.random.default_rng(abs(hash((enc, shape))) % (1 << 32))
+    raw = rng.integers(0, 65536, shape, dtype=np.uint16)
+    if shape == (480, 640):
+        raw[:100] = rng.integers(0, 1024, (100, 640), dtype=np.uint16) << 6   # 10-bit sensor data, MSB-aligned
+    out = np.empty(shape + (3,), np.uint8)
+    hostsim.hs_demosaic16(P(raw.ctypes.data), ctypes.c_int(shape[0]), ctypes.c_int(shape[1]), ctypes.c_int(CFA_ID[enc[:-2] + "8"]),
+                          P(out.ctypes.data))
+    ref, renc = O.debayer16(raw, enc)
+    assert renc == "bgr8"
+    assert int((out != ref).sum()) == 0
