@@ -441,6 +441,10 @@ def run_batch(args, cfg):
             tj = json.load(f)
         if args.config == 3 and n == 64:
             traffic = tj.get("dram_bytes_per_launch_at_bench_size"); traffic_src = tj.get("source")
+            wt = tj.get("other_kernels", {}).get("k_fused_strip<gamma, BGR8> (witness)")
+            if witness and wt:
+                witness["traffic"] = wt.get("dram_bytes_per_launch")
+                witness["algorithmic_bytes_per_launch"] = wt.get("algorithmic_bytes_per_launch")
     except Exception:
         pass
     ceiling = copy_ceiling(world)

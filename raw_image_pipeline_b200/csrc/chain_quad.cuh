@@ -45,6 +45,8 @@ RIP_HD Quad32 lds_u128(taddr a) {
 template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return prmt(w, base, 0x7650u + K); }
 // base + (v & mask); base % (mask + 1 rounded up to a power of two) == 0
 RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return (v & mask) | base; }
+// the same with the byte chosen at run time: sel = 0x7650 + byte number
+RIP_HD taddr taddr_byte_sel(taddr base, uint32_t w, uint32_t sel) { return prmt(w, base, sel); }
 #else
 typedef const uint8_t* taddr;
 RIP_HD uint32_t lds_u8(taddr a) { return *a; }
@@ -54,6 +56,7 @@ RIP_HD Pair32 lds_u64(taddr a) { Pair32 v; memcpy(&v, a, 8); return v; }
 RIP_HD Quad32 lds_u128(taddr a) { Quad32 v; memcpy(&v, a, 16); return v; }
 template <int K> RIP_HD taddr taddr_byte(taddr base, uint32_t w) { return base + ((w >> (8 * K)) & 255u); }
 RIP_HD taddr taddr_masked(taddr base, uint32_t v, uint32_t mask) { return base + (v & mask); }
+RIP_HD taddr taddr_byte_sel(taddr base, uint32_t w, uint32_t sel) { return base + ((w >> (8 * (sel & 3u))) & 255u); }
 #endif
 // base + 4 * byte K of w (a table of 32-bit entries); base % 1024 == 0
 template <int K> RIP_HD taddr taddr_byte4(taddr base, uint32_t w) {

@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(NT, 4) k_fused_fast(const __grid_constant__ Fr
   // static shared memory (< 48 KB): table addresses are link-time constants, so lookups are `LDS [index + constant]`
   __shared__ FastSmem<BGRX> sm;
   constexpr int OUT_PITCH = OutFmt<BGRX>::PITCH;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps what derives from it (row number,
+  // CFA phase selectors, row predicates) in uniform registers
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int tiles_x = (P.cols + TW - 1) / TW, tiles_y = (P.rows + TH - 1) / TH;
   const long long tiles_per_frame = (long long)tiles_x * tiles_y;
   const long long total = tiles_per_frame * P.n_frames;
@@ -405,7 +407,7 @@ __device__ __noinline__ uint32_t remap_tile_pixel_slow(const RemapParams& P, con
 __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_constant__ RemapParams P, const __grid_constant__ CUtensorMap src_map) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   RemapTileSmem& sm = *reinterpret_cast<RemapTileSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   const int tiles_x = (P.ocols + RT_W - 1) / RT_W, tiles_y = (P.orows + RT_H - 1) / RT_H;
   const long long tiles_per_frame = (long long)tiles_x * tiles_y;
   const long long total = tiles_per_frame * P.n_frames;

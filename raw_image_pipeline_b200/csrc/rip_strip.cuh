@@ -80,6 +80,49 @@ __device__ __forceinline__ void copy_table_range(uint8_t* sm, const uint8_t* blo
   for (int i = lo / 16 + tid; i < hi / 16; i += NT) dst[i] = __ldg(src + i);
 }
 
+// three staging words of one lane and row (12 bytes, lane stride 3 words: conflict-free), by shared-window address
+__device__ __forceinline__ void sts_row12(uint32_t a, uint32_t w0, uint32_t w1, uint32_t w2) {
+  asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;" ::"r"(a), "r"(w0), "r"(w1), "r"(w2) : "memory");
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {  // IMAD: the multiply-add pipe, not the integer ALU
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Stage sets whose chain is table lookups on bytes only (none / white balance / gamma / both; no colour calibration, Lab
+// or HSV step).  The four pixels of a quad are taken out of the packed channel words with per-lane byte selectors that
+// already contain the frame-edge column replication and, for a rotated frame, the reversed pixel order -- neither costs
+// an instruction per row -- and the output words are assembled by multiply-adds.  out[j] = byte j of the selectors' order.
+template <uint32_t STAGES, bool WBG>
+struct ByteChain {
+  uint32_t sel[4];  // 0x7650 + source byte of output pixel j
+  __device__ __forceinline__ void init(uint32_t colfix, bool rev) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sel[j] = 0x7650u + ((colfix >> (4 * (rev ? 3 - j : j))) & 15u);
+  }
+  __device__ __forceinline__ uint32_t channel(uint32_t w, int j, taddr wb, const StripTables& t, bool has_wb) const {
+    uint32_t v;
+    if ((STAGES & ST_WB) && has_wb) {
+      v = lds_u8(taddr_byte_sel(wb, w, sel[j]));
+      if (STAGES & ST_GAMMA) v = lds_u8(t.gamma + v);
+    } else if (STAGES & ST_GAMMA) {
+      v = lds_u8(taddr_byte_sel(t.gamma, w, sel[j]));
+    } else {
+      v = prmt(w, 0u, sel[j]);
+    }
+    return v;
+  }
+  __device__ __forceinline__ void lookup(uint32_t Bw, uint32_t Gw, uint32_t Rw, const StripTables& t, uint32_t b[4], uint32_t g[4], uint32_t r[4]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      b[j] = channel(Bw, j, t.wb_b, t, true);
+      g[j] = channel(Gw, j, t.wb_g, t, WBG);
+      r[j] = channel(Rw, j, t.wb_r, t, true);
+    }
+  }
+};
+
 // KEY = stage bits | KEY_WBG (the G channel has a white-balance table: ccc).  Colour calibration with a non-zero bias is
 // not handled here (launch_fused_strip's caller routes it to the tile kernel).
 constexpr uint32_t KEY_WBG = 32u;
@@ -93,11 +136,16 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
   // where the Lab / HSV chain of four pixels is already ~10 KB of code -- unrolled bodies thrash the instruction cache of
   // warps that run out of step (measured: 7.2 vs 5.5 ms per 64 x 12 MP)
   constexpr int UNR = (STAGES & (ST_VIG | ST_ENH)) ? 1 : 4;
+  constexpr bool BYTE_ONLY = (STAGES & (ST_CC | ST_VIG | ST_ENH)) == 0;
   using L = StripSmem<STAGES, BGRX>;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the warp index through a shuffle: tells the compiler it is warp-uniform, so everything derived from it (ring, staging
+  // and mbarrier addresses, TMA coordinates) lives in uniform registers instead of being re-broadcast before every TMA op
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   uint8_t* const sm = strip_smem_raw + ((0u - smem_u32(strip_smem_raw)) & 4095u);  // 4096-byte aligned shared-window address
   uint8_t* const sm_in = sm + L::OFF_IN + warp * (NS * CHUNK_B);   // this warp's ring
   uint8_t* const sm_out = sm + L::OFF_OUT + warp * (2 * GROUP_B);  // this warp's two staging groups (BGR8 only)
+  const uint32_t sm_out_a = smem_u32(sm_out);
   unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(sm + L::OFF_MBAR) + warp * NS;
   if (lane == 0) {
 #pragma unroll
@@ -158,6 +206,8 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
     const int oxb = rev ? P.cols - 4 - x : x;      // output column of the quad's lowest-address pixel
     const bool tail_quad = (STAGES & ST_ENH) && oxb >= tail_start;
     const uint32_t colfix = x == 0 ? 0x3211u : (x + 4 == P.cols ? 0x2210u : 0x3210u);  // column 0 <- 1, W-1 <- W-2
+    ByteChain<STAGES, WBG> bytes;
+    if (BYTE_ONLY) bytes.init(colfix, rev);
     const BayerPhase phase = bayer_phase(ca, P.cfa);  // "even" rows: ca, ca + 2, ...
     BayerPhaseRT phase_rt = bayer_phase_rt(ca, P.cfa);  // rolled row loop only: phase of the current centre row
 
@@ -206,12 +256,11 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
       ph ^= 1u << slot;
       rowp = reinterpret_cast<const uint32_t*>(sm_in + slot * CHUNK_B) + X_WORD0 + lane;
       const int nv = min(CH, n - done);  // rows of this chunk that exist (4 except at the end of a ragged unit)
-      uint8_t* sp = nullptr;             // BGR8: this lane's place in the staging row being filled
+      uint32_t sp = 0;                   // BGR8: this lane's place in the staging row being filled (shared-window address)
       if (!BGRX) {
         if (lane == 0) tma_wait_read<1>();  // the group about to be filled was handed to the TMA two groups ago
         __syncwarp();
-        sp = sm_out + obuf * GROUP_B + (rev ? (CH - 1) * OUT_ROW_B : 0) + lane_pos;
-        asm volatile("" : "+l"(sp));  // keep the address in a register: recomputing it per row costs more than holding it
+        sp = sm_out_a + obuf * GROUP_B + (rev ? (CH - 1) * OUT_ROW_B : 0) + lane_pos;
       }
       // one output row: row `tt` of the chunk.  `tc`: the row's parity when it is a compile-time constant (unrolled
       // bodies), -1 when the phase is tracked at run time (rolled loop).
@@ -228,31 +277,49 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
           demosaic_window<(t & 1) != 0>(rn, rm, rs, phase, Bw, Gw, Rw);
           rn = rm; rm = rs;
         }
-        if (colfix != 0x3210u) { Bw = prmt(Bw, 0u, colfix); Gw = prmt(Gw, 0u, colfix); Rw = prmt(Rw, 0u, colfix); }
-        float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-        if (STAGES & ST_VIG) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + voff));
-          m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
-          voff += P.vig_pitch;
-        }
-        uint32_t px[4];
-        if (!tail_quad) {
-          chain_quad<STAGES, WBG>(Bw, Gw, Rw, m, P.k, T, px);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) px[j] = chain_px_tail<STAGES>(Bw >> (8 * j), Gw >> (8 * j), Rw >> (8 * j), m[j], P.k, T);
-        }
-        if (BGRX) {
-          if (active && tt < nv) {
-            if (rev) *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[3], px[2], px[1], px[0]);
-            else *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[0], px[1], px[2], px[3]);
+        if constexpr (BYTE_ONLY) {
+          uint32_t b[4], g[4], r[4];
+          bytes.lookup(Bw, Gw, Rw, T, b, g, r);
+          if (BGRX) {
+            if (active && tt < nv) {
+              uint4 v;
+              v.x = mad_u32(r[0], 65536u, mad_u32(g[0], 256u, b[0])); v.y = mad_u32(r[1], 65536u, mad_u32(g[1], 256u, b[1]));
+              v.z = mad_u32(r[2], 65536u, mad_u32(g[2], 256u, b[2])); v.w = mad_u32(r[3], 65536u, mad_u32(g[3], 256u, b[3]));
+              *reinterpret_cast<uint4*>(outf + ooff) = v;
+            }
+            ooff += ostep;
+          } else {
+            sts_row12(sp, mad_u32(b[1], 16777216u, mad_u32(r[0], 65536u, mad_u32(g[0], 256u, b[0]))),
+                      mad_u32(g[2], 16777216u, mad_u32(b[2], 65536u, mad_u32(r[1], 256u, g[1]))),
+                      mad_u32(r[3], 16777216u, mad_u32(g[3], 65536u, mad_u32(b[3], 256u, r[2]))));
+            sp += sstep;
           }
-          ooff += ostep;
-        } else {  // lanes beyond the frame edge write staging bytes the TMA store clips
-          uint32_t* o = reinterpret_cast<uint32_t*>(sp);
-          if (rev) { o[0] = prmt(px[3], px[2], 0x4210); o[1] = prmt(px[2], px[1], 0x5421); o[2] = prmt(px[1], px[0], 0x6542); }
-          else { o[0] = prmt(px[0], px[1], 0x4210); o[1] = prmt(px[1], px[2], 0x5421); o[2] = prmt(px[2], px[3], 0x6542); }
-          sp += sstep;
+        } else {
+          if (colfix != 0x3210u) { Bw = prmt(Bw, 0u, colfix); Gw = prmt(Gw, 0u, colfix); Rw = prmt(Rw, 0u, colfix); }
+          float m[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+          if (STAGES & ST_VIG) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(P.vig + voff));
+            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+            voff += P.vig_pitch;
+          }
+          uint32_t px[4];
+          if (!tail_quad) {
+            chain_quad<STAGES, WBG>(Bw, Gw, Rw, m, P.k, T, px);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) px[j] = chain_px_tail<STAGES>(Bw >> (8 * j), Gw >> (8 * j), Rw >> (8 * j), m[j], P.k, T);
+          }
+          if (BGRX) {
+            if (active && tt < nv) {
+              if (rev) *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[3], px[2], px[1], px[0]);
+              else *reinterpret_cast<uint4*>(outf + ooff) = make_uint4(px[0], px[1], px[2], px[3]);
+            }
+            ooff += ostep;
+          } else {  // lanes beyond the frame edge write staging bytes the TMA store clips
+            if (rev) sts_row12(sp, prmt(px[3], px[2], 0x4210), prmt(px[2], px[1], 0x5421), prmt(px[1], px[0], 0x6542));
+            else sts_row12(sp, prmt(px[0], px[1], 0x4210), prmt(px[1], px[2], 0x5421), prmt(px[2], px[3], 0x6542));
+            sp += sstep;
+          }
         }
       };
       if constexpr (UNR == 1) {

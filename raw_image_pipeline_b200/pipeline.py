@@ -110,6 +110,8 @@ class RawImagePipeline:
 
     def _run(self, image: np.ndarray, encoding: str) -> Tuple[np.ndarray, str]:
         want = np.uint16 if self._reads_16bit(encoding) else np.uint8
+        if _is_16bit(encoding) and want is np.uint8 and image.ndim in (2, 3):
+            self.output_shape(image.shape, encoding)  # extension off: the reference's "valid pattern but is not supported" comes first
         if image.dtype != want or image.ndim not in (2, 3):
             raise ValueError(f"image must be a {np.dtype(want).name} array of shape (rows, cols) or (rows, cols, channels)")
         item = image.dtype.itemsize
@@ -145,6 +147,8 @@ class RawImagePipeline:
     def process_batch(self, frames: np.ndarray, encoding: str, out: Optional[np.ndarray] = None) -> np.ndarray:
         """n frames host -> host through rip_apply_batch_host (pinned memory gives full PCIe rate)."""
         want = np.uint16 if self._reads_16bit(encoding) else np.uint8
+        if _is_16bit(encoding) and want is np.uint8 and frames.ndim in (3, 4):
+            self.output_shape(frames.shape[1:], encoding)
         if frames.dtype != want or frames.ndim not in (3, 4) or not frames.flags.c_contiguous:
             raise ValueError(f"frames must be a C-contiguous {np.dtype(want).name} array (n, rows, cols[, channels])")
         n, rows, cols = frames.shape[:3]
