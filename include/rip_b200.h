@@ -152,15 +152,24 @@ RIP_API int rip_apply_batch_host(rip_pipeline* p, const uint8_t* in, size_t in_f
                          size_t out_frame_stride);
 
 /* Host-to-host over several GPUs of one box (frames are independent, so they shard with no collective):
- * `handles[i]` is a pipeline bound to its own device (rip_set_device) and configured like the others.  The batch is cut
- * into n_handles contiguous chunks (sizes differ by at most one frame; chunk i goes to handles[i]); every chunk runs
- * rip_apply_batch_host on its own host thread; returns when `out` is complete.  With CCC temporal consistency a batch
- * is ONE camera stream and must go to one pipeline: the call then fails with RIP_ERR_INVALID_ARGUMENT.  Returns the
- * first failing chunk's status (its message is in that handle's rip_last_error).  The reference has no multi-GPU path
- * (raw_image_pipeline.cpp:193-196 uploads to the one current device).                                             */
+ * `handles[i]` is a pipeline bound to its own device (rip_set_device) and configured like the others.  Every pipeline
+ * runs on its own host thread and claims the next chunk of <= 16 frames whenever one of its three copy/compute slots
+ * is free, so GPUs behind a slower host link take fewer frames instead of holding the call back (the GPUs of one box
+ * do not see the same host bandwidth: profiles/pcie_ceiling.json); returns when `out` is complete.  Every frame gets
+ * the same bytes whichever pipeline takes it.  With CCC temporal consistency a batch is ONE camera stream and must go
+ * to one pipeline: the call then fails with RIP_ERR_INVALID_ARGUMENT.  Returns the first failing pipeline's status (its
+ * message is in that handle's rip_last_error).  The reference has no multi-GPU path (raw_image_pipeline.cpp:193-196
+ * uploads to the one current device).                                                                             */
 RIP_API int rip_apply_batch_host_multi(rip_pipeline* const* handles, int n_handles, const uint8_t* in, size_t in_frame_stride,
                                int n_frames, int rows, int cols, int channels, const char* encoding, uint8_t* out,
                                size_t out_frame_stride);
+
+/* Page-locked host memory.  rip_apply copies a pageable caller image through the pipeline's own pinned staging
+ * buffers (two host copies per frame); an image / output buffer that is page-locked -- from these two calls,
+ * cudaHostAlloc or cudaHostRegister -- is read / written by the GPU's copy engines directly (the reference's
+ * cv::cuda::GpuMat::upload / download, raw_image_pipeline.cpp:193-203, behave the same way for cv::cuda::HostMem).    */
+RIP_API int rip_pinned_alloc(size_t bytes, void** ptr);
+RIP_API int rip_pinned_free(void* ptr);
 
 /* ---- inspection ---------------------------------------------------------------------------
  * Host-computed tables exactly as the kernels consume them (no GPU needed): "gamma_lut" (256 B,

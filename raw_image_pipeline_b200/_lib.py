@@ -55,6 +55,8 @@ SIGNATURES = {
                                        c_size_t, c_void_p, c_void_p]),
     "rip_apply_batch_host": (c_int, [_H, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_char_p, c_void_p,
                                      c_size_t]),
+    "rip_pinned_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "rip_pinned_free": (c_int, [c_void_p]),
     "rip_apply_batch_host_multi": (c_int, [POINTER(_H), c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_char_p, c_void_p,
                                            c_size_t]),
     "rip_debug_table": (c_int, [_H, c_char_p, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),

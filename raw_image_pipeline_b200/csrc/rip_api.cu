@@ -250,6 +250,16 @@ namespace {
     if (_e != cudaSuccess) return (p)->cuda_fail(_e, #expr); \
   } while (0)
 
+// Host-built tables (colour tables, vignetting mask, undistortion maps) go to the device on the pipeline's own stream and
+// the call waits for it.  A plain cudaMemcpy from pageable memory returns once the data sits in the driver's staging
+// buffer -- the tail of the DMA may still be in flight, and the pipeline's streams are non-blocking, i.e. not ordered
+// behind the legacy stream such a copy runs on: the first kernel after a table build could read the tail of a table
+// before it arrived (seen as wrong bottom rows in the first frame after a rebuild).
+static cudaError_t upload_tables(rip_pipeline* p, void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(p->stream);
+}
+
 int ensure_cuda(rip_pipeline* p) {
   if (p->cuda_ready) {
     RIP_CUDA(p, cudaSetDevice(p->device));
@@ -371,11 +381,11 @@ int ensure_tables(rip_pipeline* p) {
   build_chain_blob(key, blob.data());
   RIP_CUDA(p, cudaDeviceSynchronize());  // nothing in flight may still read the old tables
   RIP_CUDA(p, p->d_tables.reserve(TABLE_BYTES));
-  RIP_CUDA(p, cudaMemcpy(p->d_tables.ptr, blob.data(), TABLE_BYTES, cudaMemcpyHostToDevice));
+  RIP_CUDA(p, upload_tables(p, p->d_tables.ptr, blob.data(), TABLE_BYTES));
   std::vector<uint8_t> sblob(STRIP_BLOB_BYTES, 0);
   build_strip_blob(blob.data(), sblob.data());
   RIP_CUDA(p, p->d_strip_tables.reserve(STRIP_BLOB_BYTES));
-  RIP_CUDA(p, cudaMemcpy(p->d_strip_tables.ptr, sblob.data(), STRIP_BLOB_BYTES, cudaMemcpyHostToDevice));
+  RIP_CUDA(p, upload_tables(p, p->d_strip_tables.ptr, sblob.data(), STRIP_BLOB_BYTES));
   p->tables_valid = true; p->tables_key = key;
   return RIP_OK;
 }
@@ -405,7 +415,7 @@ int ensure_vignetting(rip_pipeline* p, int rows, int cols, int angle) {
   // four rows of padding (1.0f): the strip kernel reads the mask rows of a whole 4-row chunk even where the frame ends inside it
   full.resize(full.size() + (size_t)4 * cols, 1.0f);
   RIP_CUDA(p, p->d_vig.reserve(full.size() * sizeof(float)));
-  RIP_CUDA(p, cudaMemcpy(p->d_vig.ptr, full.data(), full.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RIP_CUDA(p, upload_tables(p, p->d_vig.ptr, full.data(), full.size() * sizeof(float)));
   p->vig_rows = rows; p->vig_cols = cols; p->vig_angle = angle; p->vig_pitch = cols; memcpy(p->vig_par, par, sizeof par);
   return RIP_OK;
 }
@@ -424,7 +434,7 @@ int ensure_map(rip_pipeline* p) {
   build_host_map(p);
   RIP_CUDA(p, cudaDeviceSynchronize());
   RIP_CUDA(p, p->d_map.reserve(p->h_map.size() * sizeof(float)));
-  RIP_CUDA(p, cudaMemcpy(p->d_map.ptr, p->h_map.data(), p->h_map.size() * sizeof(float), cudaMemcpyHostToDevice));
+  RIP_CUDA(p, upload_tables(p, p->d_map.ptr, p->h_map.data(), p->h_map.size() * sizeof(float)));
   p->map_epoch = p->hs.und_epoch;
   return RIP_OK;
 }
@@ -460,11 +470,11 @@ int ensure_packed_map(rip_pipeline* p, int src_rows, int src_cols) {
   if (p->pmap_ok) {
     RIP_CUDA(p, cudaDeviceSynchronize());
     RIP_CUDA(p, p->d_pmap.reserve(packed.size() * sizeof(uint32_t)));
-    RIP_CUDA(p, cudaMemcpy(p->d_pmap.ptr, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RIP_CUDA(p, upload_tables(p, p->d_pmap.ptr, packed.data(), packed.size() * sizeof(uint32_t)));
     RIP_CUDA(p, p->d_tiles.reserve(table.size() * sizeof(int)));
-    RIP_CUDA(p, cudaMemcpy(p->d_tiles.ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+    RIP_CUDA(p, upload_tables(p, p->d_tiles.ptr, table.data(), table.size() * sizeof(int)));
     RIP_CUDA(p, p->d_tmap.reserve(padded.size() * sizeof(uint32_t)));
-    RIP_CUDA(p, cudaMemcpy(p->d_tmap.ptr, padded.data(), padded.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RIP_CUDA(p, upload_tables(p, p->d_tmap.ptr, padded.data(), padded.size() * sizeof(uint32_t)));
     p->tmap_pitch = pitch;
   }
   p->pmap_epoch = p->hs.und_epoch; p->pmap_src_rows = src_rows; p->pmap_src_cols = src_cols;
@@ -954,6 +964,28 @@ cudaError_t reserve_pinned(uint8_t*& ptr, size_t& cap, size_t n) {
 // TMA-staged tile undistortion, like the batch entry points) and the D2H copy run as ONE CUDA-graph launch from the second
 // frame of a (shape, configuration) on, and the result is copied out of pinned memory the same way.  The pre-undistortion
 // colour image is no longer produced on the way: getDistColorImage() recomputes it on demand from the retained input.
+}  // extern "C"
+
+// page-locked host memory the copy engines can address directly (cudaHostAlloc / cudaHostRegister / rip_pinned_alloc)
+static bool host_pointer_is_pinned(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" {
+
+int rip_pinned_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return RIP_ERR_INVALID_ARGUMENT;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) == cudaSuccess ? RIP_OK : RIP_ERR_CUDA;
+}
+
+int rip_pinned_free(void* ptr) {
+  if (!ptr) return RIP_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? RIP_OK : RIP_ERR_CUDA;
+}
+
 int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int channels, size_t step, char* encoding,
               size_t encoding_capacity, uint8_t* out, size_t out_capacity, int* out_rows, int* out_cols, int* out_channels) {
   if (!data || !out || !encoding) return p->fail(RIP_ERR_INVALID_ARGUMENT, "null argument");
@@ -971,27 +1003,32 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   if (!step) step = row_bytes;
   RIP_CUDA(p, p->d_in.reserve(pitch * rows));
   RIP_CUDA(p, p->d_out.reserve(out_bytes));
-  RIP_CUDA(p, reserve_pinned(p->h_stage_in, p->h_stage_in_cap, pitch * rows));
-  RIP_CUDA(p, reserve_pinned(p->h_stage_out, p->h_stage_out_cap, out_bytes));
+  // Page-locked caller buffers (rip_pinned_alloc, cudaHostAlloc, cudaHostRegister) are read / written by the copy engines
+  // directly; pageable ones go through the pipeline's own pinned staging buffers.
+  const bool direct_in = step == pitch && host_pointer_is_pinned(data);
+  const bool direct_out = host_pointer_is_pinned(out);
+  if (!direct_in) RIP_CUDA(p, reserve_pinned(p->h_stage_in, p->h_stage_in_cap, pitch * rows));
+  if (!direct_out) RIP_CUDA(p, reserve_pinned(p->h_stage_out, p->h_stage_out_cap, out_bytes));
   auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now_us();
   // caller's image -> pinned staging (rows re-pitched to a multiple of 16 bytes: the TMA fast path)
-  if (step == pitch) CopyPool::get().copy(p->h_stage_in, data, pitch * rows, /*pinned_side=*/0);
+  if (direct_in) RIP_CUDA(p, cudaMemcpyAsync(p->d_in.ptr, data, pitch * rows, cudaMemcpyHostToDevice, p->stream));
+  else if (step == pitch) CopyPool::get().copy(p->h_stage_in, data, pitch * rows, /*pinned_side=*/0);
   else { for (int y = 0; y < rows; ++y) memcpy(p->h_stage_in + (size_t)y * pitch, data + (size_t)y * step, row_bytes); demote_range(p->h_stage_in, pitch * rows); }
 
-  auto enqueue = [&]() -> int {  // everything between the two host copies, on p->stream
-    RIP_CUDA(p, cudaMemcpyAsync(p->d_in.ptr, p->h_stage_in, pitch * rows, cudaMemcpyHostToDevice, p->stream));
+  auto enqueue = [&]() -> int {  // everything between the two host copies, on p->stream (copies of caller-owned pinned buffers stay outside: their addresses change per call)
+    if (!direct_in) RIP_CUDA(p, cudaMemcpyAsync(p->d_in.ptr, p->h_stage_in, pitch * rows, cudaMemcpyHostToDevice, p->stream));
     int r = process_device(p, p->scratch, g, p->d_in.as<uint8_t>(), pitch, pitch * rows, 1, p->d_out.as<uint8_t>(), out_bytes, nullptr, 0,
                            false, p->stream, /*keep_bgr_color=*/false);
     if (r != RIP_OK) return r;
-    RIP_CUDA(p, cudaMemcpyAsync(p->h_stage_out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (!direct_out) RIP_CUDA(p, cudaMemcpyAsync(p->h_stage_out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
     return RIP_OK;
   };
   // CCC keeps host-side state per frame (tracker reset flag, result pointers), profiling records events: both stay un-captured
   const bool graph_ok = p->use_graph && !p->profile && wbk != 2;
   rip_pipeline::GraphKey key;
   key.rows = rows; key.cols = cols; key.channels = channels; key.encoding = encoding; key.epoch = p->config_epoch;
-  key.d_in = p->d_in.ptr; key.d_out = p->d_out.ptr; key.h_in = p->h_stage_in; key.h_out = p->h_stage_out;
+  key.d_in = p->d_in.ptr; key.d_out = p->d_out.ptr; key.h_in = direct_in ? nullptr : p->h_stage_in; key.h_out = direct_out ? nullptr : p->h_stage_out;
   bool launched = false;
   const double t1 = now_us();
   if (graph_ok && p->graph_exec && key == p->graph_key_full()) {
@@ -1024,6 +1061,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
              if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; } }
     }
   }
+  if (direct_out) RIP_CUDA(p, cudaMemcpyAsync(out, p->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, p->stream));
   const double t1b = now_us();
   if (wbk == 1) RIP_CUDA(p, cudaMemcpyAsync(p->last_pca, p->scratch.coeff.ptr, sizeof p->last_pca, cudaMemcpyDeviceToHost, p->stream));
   if (wbk == 2 && (rc = ccc_fetch_last(p->ccc, p->scratch.gains, p->stream, p->last_error)) != RIP_OK) return rc;
@@ -1031,7 +1069,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   const double t2 = now_us();
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
   const double t3 = now_us();
-  CopyPool::get().copy(out, p->h_stage_out, out_bytes, /*pinned_side=*/1);
+  if (!direct_out) CopyPool::get().copy(out, p->h_stage_out, out_bytes, /*pinned_side=*/1);
   const double t4 = now_us();
   p->apply_us[0] = t1 - t0; p->apply_us[1] = t1b - t1; p->apply_us[2] = t2 - t1b; p->apply_us[3] = t3 - t2; p->apply_us[4] = t4 - t3;
   p->have_frame = true; p->last_geom = g; p->last_in_encoding = encoding;

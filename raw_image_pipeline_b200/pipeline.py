@@ -10,6 +10,7 @@ get_processed_image; and the batch entry points process_batch / process_batch_de
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -34,6 +35,61 @@ def _is_16bit(encoding: str) -> bool:
     return encoding in ("bayer_rggb16", "bayer_bggr16", "bayer_gbrg16", "bayer_grbg16")
 
 
+class _PinnedPool:
+    """Result arrays of process() backed by page-locked memory (rip_pinned_alloc): the GPU's copy engine writes the frame
+    straight into the array the caller receives, instead of into a staging buffer that is then copied (and page-faulted)
+    into a fresh pageable array.  A buffer goes back to the pool when the last array viewing it is garbage-collected;
+    when the caller holds on to more results than the pool is allowed to pin, process() falls back to pageable arrays."""
+
+    MAX_BYTES = 512 << 20
+    MAX_SLOTS = 16
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._free = []   # (ptr, capacity)
+        self._total = 0
+        self._slots = 0
+        self._closed = False
+
+    def take(self, nbytes: int):
+        for i, (ptr, cap) in enumerate(self._free):
+            if cap >= nbytes:
+                del self._free[i]
+                return self._wrap(ptr, cap, nbytes)
+        if self._slots >= self.MAX_SLOTS or self._total + nbytes > self.MAX_BYTES:
+            if not self._free:
+                return None
+            ptr, cap = self._free.pop()   # too small for this frame size: replace it
+            self._lib.rip_pinned_free(ptr)
+            self._total -= cap
+            self._slots -= 1
+            if self._total + nbytes > self.MAX_BYTES:
+                return None
+        ptr = ctypes.c_void_p()
+        if self._lib.rip_pinned_alloc(nbytes, ctypes.byref(ptr)) != L.RIP_OK or not ptr.value:
+            return None
+        self._total += nbytes
+        self._slots += 1
+        return self._wrap(ptr.value, nbytes, nbytes)
+
+    def _wrap(self, ptr: int, cap: int, nbytes: int) -> np.ndarray:
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, ptr, cap)   # runs when the last array viewing `buf` is gone
+        return np.frombuffer(buf, np.uint8)
+
+    def _release(self, ptr: int, cap: int):
+        if self._closed:
+            self._lib.rip_pinned_free(ptr)
+        else:
+            self._free.append((ptr, cap))
+
+    def close(self):
+        self._closed = True
+        for ptr, _ in self._free:
+            self._lib.rip_pinned_free(ptr)
+        self._free = []
+
+
 class RawImagePipeline:
     def __init__(self, use_gpu: bool = False, params_path: Optional[str] = None, calibration_path: str = "",
                  color_calibration_path: str = "", device: Optional[int] = None):
@@ -51,8 +107,13 @@ class RawImagePipeline:
             _raise(rc, (self._lib.rip_last_error(None) or b"").decode())
         if device is not None:
             self._check(self._lib.rip_set_device(self._h, int(device)))
+        self._pool = _PinnedPool(self._lib)
+        self.use_pinned_results = True   # process() returns arrays backed by page-locked memory (see _PinnedPool)
 
     def __del__(self):
+        pool = getattr(self, "_pool", None)
+        if pool is not None:
+            pool.close()
         h = getattr(self, "_h", None)
         if h:
             self._lib.rip_destroy(h)
@@ -99,6 +160,14 @@ class RawImagePipeline:
         out = np.array(arr[:n.value], dtype=np.float64)
         return out.reshape(shape) if shape else out
 
+    def pinned_empty(self, shape, dtype=np.uint8) -> Optional[np.ndarray]:
+        """An uninitialised array in page-locked memory from the pipeline's pool (None when the pool is exhausted): frames
+        placed in such an array are uploaded by the copy engine directly, without the staging copy of pageable images."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        flat = self._pool.take(n)
+        return None if flat is None else flat.view(dt).reshape(shape)
+
     # ---- main interfaces ---------------------------------------------------------------------
     def output_shape(self, image_shape: Tuple[int, ...], encoding: str) -> Tuple[int, int, int]:
         rows, cols = image_shape[0], image_shape[1]
@@ -120,7 +189,9 @@ class RawImagePipeline:
         rows, cols = img.shape[0], img.shape[1]
         ch = img.shape[2] if img.ndim == 3 else 1
         orows, ocols, och = self.output_shape(img.shape, encoding)
-        out = np.empty((orows, ocols, och), np.uint8)
+        # page-locked when the pool has room: no staging copy on the way out
+        flat = self._pool.take(orows * ocols * och) if self.use_pinned_results else None
+        out = flat.reshape(orows, ocols, och) if flat is not None else np.empty((orows, ocols, och), np.uint8)
         enc = ctypes.create_string_buffer(encoding.encode(), 64)
         r, c, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._check(self._lib.rip_apply(self._h, img.ctypes.data, rows, cols, ch, img.strides[0], enc, 64,

@@ -136,3 +136,36 @@ def test_16bit_bayer_extension(oracle_built, enc, flip):
     for i in range(3):
         assert_same(batch[i], refs[i], f"{enc} flip {flip} batch frame {i}")
     assert p.output_shape((rows, cols), enc)[2] == 3
+
+
+def test_pinned_and_pageable_buffers(oracle_built):
+    """rip_apply with page-locked caller buffers (copy engines address them directly) and with pageable ones (staged through
+    the pipeline's pinned buffers) gives the same bytes; results of process() come from the pinned pool and go back to it."""
+    rows, cols = 480, 640
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (6, rows, cols), dtype=np.uint8)
+    p, o = make_pair(rows, cols, **FULL)
+    refs = [o.apply(f, "bayer_bggr8")[0] for f in frames]
+    pin_in = p.pinned_empty((rows, cols))
+    assert pin_in is not None
+    held = []
+    for mode in ("pageable-out", "pinned-out", "pinned-in"):
+        p.use_pinned_results = mode != "pageable-out"
+        for i, f in enumerate(frames):
+            src = f
+            if mode == "pinned-in":
+                pin_in[...] = f
+                src = pin_in
+            out = p.process(src, "bayer_bggr8")
+            assert_same(out, refs[i], f"{mode} frame {i}")
+            held.append(out)   # results stay valid while the caller holds them, whatever later calls do
+    for k, out in enumerate(held):
+        assert_same(out, refs[k % len(frames)], f"held result {k}")
+    # the pool has a bound: holding more results than it may pin falls back to pageable arrays, transparently
+    many = [p.process(frames[0], "bayer_bggr8") for _ in range(p._pool.MAX_SLOTS + 4)]
+    for out in many:
+        assert_same(out, refs[0], "beyond the pool")
+    del many, held
+    import gc
+    gc.collect()
+    assert len(p._pool._free) >= 1
