@@ -60,11 +60,13 @@ class MultiGpuPipeline:
         return sum(r.kernel_launches() for r in self.replicas)
 
     def shard(self, n_frames: int):
-        """[(begin, end)] per GPU: contiguous chunks whose sizes differ by at most one (sharding.shard_range)."""
+        """[(begin, end)] per GPU: contiguous chunks whose sizes differ by at most one (sharding.shard_range) -- the split
+        process_streams and the torchrun bench use; process_batch deals chunks on demand instead."""
         return [shard_range(n_frames, i, self.n_gpus) for i in range(self.n_gpus)]
 
     def process_batch(self, frames: np.ndarray, encoding: str, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """n frames host -> host, chunk i on GPU i (rip_apply_batch_host_multi)."""
+        """n frames host -> host over all GPUs (rip_apply_batch_host_multi: chunks of <= 16 frames claimed on demand by the
+        pipelines' worker threads, so GPUs behind a slower host link take fewer frames)."""
         if frames.dtype != np.uint8 or frames.ndim not in (3, 4) or not frames.flags.c_contiguous:
             raise ValueError("frames must be a C-contiguous uint8 array (n, rows, cols[, channels])")
         n, rows, cols = frames.shape[:3]

@@ -16,8 +16,12 @@ n_dev = torch.cuda.device_count()
 per_gpu = int(os.environ.get("FRAMES_PER_GPU", "64"))
 base = bench.make_frames(16, rows, cols, 5000, enc=enc)
 results = []
+only = [int(x) for x in os.environ.get("ONLY_GPUS", "").split(",") if x]
 g = 1
 while g <= n_dev:
+    if only and g not in only:
+        g *= 2
+        continue
     n = per_gpu * g
     h_in = torch.from_numpy(np.concatenate([base] * ((n + 15) // 16))[:n]).pin_memory()
     h_out = torch.empty((n, rows, cols, 3), dtype=torch.uint8).pin_memory()
@@ -35,6 +39,7 @@ while g <= n_dev:
     mp.set_undistortion(True)
     for _ in range(2):
         mp.process_batch_ptr(h_in.data_ptr(), n, rows, cols, 1, enc, h_out.data_ptr())
+    launches0 = [r.kernel_launches() for r in mp.replicas]
     t0 = time.perf_counter()
     reps = 3
     for _ in range(reps):
@@ -45,7 +50,10 @@ while g <= n_dev:
     for i in (0, n - 1):
         ref, _ = o.apply(h_in[i].numpy(), enc)
         bad += int(np.count_nonzero(h_out[i].numpy() != ref))
-    results.append({"gpus": g, "frames": n, "mpix_per_s": n * rows * cols / dt / 1e6, "ms": dt * 1e3, "differing_values_vs_oracle": bad})
+    launches = [r.kernel_launches() - l0 for r, l0 in zip(mp.replicas, launches0)]
+    share = [round(l / max(1, sum(launches)), 3) for l in launches]   # kernel launches are proportional to the chunks a GPU took
+    results.append({"gpus": g, "frames": n, "mpix_per_s": n * rows * cols / dt / 1e6, "ms": dt * 1e3, "differing_values_vs_oracle": bad,
+                    "share_of_work_per_gpu": share})
     del mp, h_in, h_out
     g *= 2
-print(json.dumps({"entry": "rip_apply_batch_host_multi (one process, one host thread per GPU)", "workload": cfg["workload"], "results": results}))
+print(json.dumps({"entry": "rip_apply_batch_host_multi (one process, one host thread per GPU, chunks of <= 16 frames claimed on demand)", "workload": cfg["workload"], "results": results}))
