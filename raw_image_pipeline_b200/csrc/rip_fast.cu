@@ -14,6 +14,7 @@
 // Everything else (ragged widths, unaligned buffers, 90/270 rotations, 3-channel inputs) takes the
 // generic kernels in rip_kernels.cu; both produce identical bytes.
 #include <cuda.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -337,28 +338,37 @@ __global__ void __launch_bounds__(NT) k_pca_stats_fast(const __grid_constant__ F
     constexpr int RPW = TH_STATS / 8;
     const int ya = max(c.y0 + RPW * warp, 1), yb = min(c.y0 + RPW * warp + RPW - 1, P.rows - 2);
     if (x < P.cols && ya <= yb) {
-      BayerRow rn = load_bayer_row(s_in + (ya - 1 - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, ya - 1, P.cfa);
-      BayerRow rm = load_bayer_row(s_in + (ya - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, ya, P.cfa);
-#pragma unroll 4
-      for (int k = 0; k < RPW; ++k) {
-        const int y = ya + k;
-        if (y <= yb) {
-          const BayerRow rs = load_bayer_row(s_in + (y + 1 - c.y0 + 1) * IN_WORDS + IN_X_WORD0 + lane, y + 1, P.cfa);
-          uint32_t Bw, Gw, Rw;
-          demosaic_window(rn, rm, rs, y, P.cfa, Bw, Gw, Rw);
-          if (x == 0 || x + 4 == P.cols) {  // frame border columns: column 0 <- column 1, column W-1 <- column W-2
-            const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
-            Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix);
-          }
-          const uint32_t mult = 1u + (y == 1) + (y == P.rows - 2);
-          const uint32_t ones = 0x01010101u * mult;
+      // CFA phase of the rows ya, ya + 2, ... computed once per tile; the rows in between use it mirrored (bayer_window.cuh)
+      const BayerPhase ph = bayer_phase(ya, P.cfa);
+      const uint32_t* const row0 = s_in + (1 - c.y0) * IN_WORDS + IN_X_WORD0 + lane;  // staged row of frame row 0
+      BayerRow rn = load_bayer_row<true>(row0 + (ya - 1) * IN_WORDS, ph);
+      BayerRow rm = load_bayer_row<false>(row0 + ya * IN_WORDS, ph);
+      const bool edge_col = x == 0 || x + 4 == P.cols;  // frame border columns: column 0 <- column 1, column W-1 <- column W-2
+      const uint32_t fix = x == 0 ? 0x3211u : 0x2210u;
+      auto row_step = [&](auto odd_tag, int y) {
+        constexpr bool ODD = decltype(odd_tag)::value;
+        if (y > yb) return;
+        const BayerRow rs = load_bayer_row<!ODD>(row0 + (y + 1) * IN_WORDS, ph);
+        uint32_t Bw, Gw, Rw;
+        demosaic_window<ODD>(rn, rm, rs, ph, Bw, Gw, Rw);
+        if (edge_col) { Bw = prmt(Bw, 0u, fix); Gw = prmt(Gw, 0u, fix); Rw = prmt(Rw, 0u, fix); }
+        sb = dp4a_u(Bw, 0x01010101u, sb); sr = dp4a_u(Rw, 0x01010101u, sr); sg = dp4a_u(Gw, 0x01010101u, sg);
+        tb2 = dp4a_u(Bw, Bw, tb2); tr2 = dp4a_u(Rw, Rw, tr2);
+        if (y == 1 || y == P.rows - 2) {  // these rows also stand for the frame's first / last row (both when H == 3)
+          const uint32_t extra = (uint32_t)(y == 1) + (uint32_t)(y == P.rows - 2);
+          const uint32_t ones = 0x01010101u * extra;
           sb = dp4a_u(Bw, ones, sb); sr = dp4a_u(Rw, ones, sr); sg = dp4a_u(Gw, ones, sg);
-          tb2 += mult * dp4a_u(Bw, Bw, 0u); tr2 += mult * dp4a_u(Rw, Rw, 0u);
-          mx_b = __vimax3_u16x2(mx_b, lanes16(Bw, 0), lanes16(Bw, 1));
-          mx_g = __vimax3_u16x2(mx_g, lanes16(Gw, 0), lanes16(Gw, 1));
-          mx_r = __vimax3_u16x2(mx_r, lanes16(Rw, 0), lanes16(Rw, 1));
-          rn = rm; rm = rs;
+          tb2 += extra * dp4a_u(Bw, Bw, 0u); tr2 += extra * dp4a_u(Rw, Rw, 0u);
         }
+        mx_b = __vimax3_u16x2(mx_b, lanes16(Bw, 0), lanes16(Bw, 1));
+        mx_g = __vimax3_u16x2(mx_g, lanes16(Gw, 0), lanes16(Gw, 1));
+        mx_r = __vimax3_u16x2(mx_r, lanes16(Rw, 0), lanes16(Rw, 1));
+        rn = rm; rm = rs;
+      };
+#pragma unroll 2
+      for (int k = 0; k < RPW; k += 2) {
+        row_step(std::false_type{}, ya + k);
+        row_step(std::true_type{}, ya + k + 1);
       }
     }
     sb2 += tb2; sr2 += tr2;
