@@ -38,10 +38,15 @@ def main():
             p.process(frames[0], enc)
             assert p.get_rect_mask().shape == (rows, cols)
     # light stage sets (strip kernel, BGR8 staging + TMA stores), ragged height
-    for kw in (dict(gamma=0.8), dict(wb="pca", gamma=0.8), dict(flip=180)):
+    for kw in (dict(gamma=0.8), dict(wb="pca", gamma=0.8), dict(flip=180), dict(wb="ccc", gamma=0.8, flip=180), dict(wb="pca", cc=True, gamma=0.8)):
         p, o = make_pair(163, 400, **kw)
         raw = synth.bayer_frame(163, 400, enc, 9200, "U")
         bad += int(np.count_nonzero(p.process_batch(raw[None], enc)[0] != o.apply(raw, enc)[0]))
+    # 16-bit Bayer extension (k_bayer16_to_bgr8 + the 3-channel chain)
+    p, o = make_pair(166, 400, **FULL)
+    p.set_debayer_allow_16bit(True); o.p.debayer_allow_16bit = True
+    raw16 = (np.random.default_rng(9300).integers(0, 4096, (166, 400), dtype=np.uint16) << 4)
+    bad += int(np.count_nonzero(p.process(raw16, "bayer_rggb16") != o.apply(raw16, "bayer_rggb16")[0]))
     print("sanitize workload: values differing from the oracle =", bad)
     return 1 if bad else 0
 
