@@ -4,7 +4,7 @@
 //   k_ccc_hist      360x270 bilinear resample of the debayered+flipped frame (only the 4 source
 //                   pixels each sample touches are demosaiced) -> log-chroma bin -> integer counts
 //   k_ccc_weights   counts -> the fp32 value `count` sequential additions of 1/97200 produce
-//   k_ccc_fft       256-point radix-2 FFT of one row in shared memory (fp64), output transposed;
+//   k_ccc_fft       256-point radix-2 FFTs of eight rows per CTA in shared memory (fp64), output transposed;
 //                   four passes give  IDFT2( DFT2(hist) * DFT2(filter) )   (ccc.cpp:273-298)
 //   k_ccc_argmax    + bias, first maximum in row-major order (cv::minMaxLoc)
 //   k_ccc_gains     [Kalman tracker ->] gains (ccc.cpp:300-381)
@@ -28,7 +28,7 @@ namespace {
 
 constexpr int N_SMALL = CCC_SMALL_W * CCC_SMALL_H;  // 97200
 constexpr int N_BINS2 = CCC_BINS * CCC_BINS;        // 65536
-constexpr int CHUNK = 16;                           // frames per FFT batch (2 x 16 MB of spectra)
+constexpr int CHUNK = 64;                           // frames per FFT batch (2 x 64 MB of spectra)
 
 struct KfState {
   float x[2];
@@ -84,49 +84,67 @@ __global__ void __launch_bounds__(256) k_ccc_weights(const unsigned* __restrict_
   if (i < n) hist[i] = weight[min(counts[i], (unsigned)N_SMALL)];
 }
 
-// One 256-point FFT per CTA (128 threads, one butterfly each per stage), output transposed.
+// Eight 256-point FFTs (eight consecutive rows of one frame) per CTA of 256 threads, radix 2 in shared memory (fp64),
+// output transposed: with eight rows in flight every transposed output row receives 128 contiguous bytes per CTA (one row
+// per CTA wrote 16-byte pieces 4 KB apart), and a stage's twiddle factor is loaded once per thread for its four butterflies.
 //   MODE 0: real fp32 input, forward        MODE 1: complex input, forward
 //   MODE 2: complex input multiplied by `mul` (the filter spectrum), inverse (unnormalised)
 //   MODE 3: complex input, inverse (unnormalised)
+constexpr int FFT_ROWS = 8;     // rows per CTA
+constexpr int FFT_PITCH = 257;  // double2 per shared row: the odd pitch makes the transposed read-out conflict-free
 template <int MODE>
-__global__ void __launch_bounds__(128) k_ccc_fft(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw,
+__global__ void __launch_bounds__(256) k_ccc_fft(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw,
                                                  const double2* __restrict__ mul) {
-  __shared__ double2 s[256];
-  const int row = blockIdx.x, t = threadIdx.x;
+  __shared__ double2 s[FFT_ROWS * FFT_PITCH];
+  __shared__ double2 s_tw[128];
+  const int row0 = blockIdx.x * FFT_ROWS, t = threadIdx.x;
   const size_t base = (size_t)blockIdx.y * N_BINS2;
+  if (t < 128) {
+    double2 w = tw[t];
+    if (MODE >= 2) w.y = -w.y;
+    s_tw[t] = w;
+  }
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int e = t + 128 * k;
+  for (int r = 0; r < FFT_ROWS; ++r) {  // row r, element t: coalesced
+    const size_t idx = (size_t)(row0 + r) * 256 + t;
     double2 v;
     if (MODE == 0) {
-      v.x = (double)static_cast<const float*>(in)[base + row * 256 + e];
+      v.x = (double)static_cast<const float*>(in)[base + idx];
       v.y = 0.0;
     } else {
-      v = static_cast<const double2*>(in)[base + row * 256 + e];
+      v = static_cast<const double2*>(in)[base + idx];
       if (MODE == 2) {
-        const double2 m = mul[row * 256 + e];
+        const double2 m = mul[idx];
         v = make_double2(v.x * m.x - v.y * m.y, v.x * m.y + v.y * m.x);
       }
     }
-    s[__brev((unsigned)e) >> 24] = v;
+    s[r * FFT_PITCH + (__brev((unsigned)t) >> 24)] = v;
   }
   __syncthreads();
+  // butterfly b of rows (t >> 7) + {0, 2, 4, 6}
+  const int b = t & 127;
+  double2* const sr = s + (t >> 7) * FFT_PITCH;
 #pragma unroll
   for (int half = 1; half < 256; half <<= 1) {
-    const int pos = t & (half - 1);
-    const int i = ((t - pos) << 1) + pos, j = i + half;
-    double2 w = tw[pos * (128 / half)];
-    if (MODE >= 2) w.y = -w.y;
-    const double2 a = s[i], b = s[j];
-    const double2 bw = make_double2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-    s[i] = make_double2(a.x + bw.x, a.y + bw.y);
-    s[j] = make_double2(a.x - bw.x, a.y - bw.y);
+    const int pos = b & (half - 1);
+    const int i = ((b - pos) << 1) + pos, j = i + half;
+    const double2 w = s_tw[pos * (128 / half)];
+#pragma unroll
+    for (int k = 0; k < FFT_ROWS / 2; ++k) {
+      double2* const q = sr + 2 * k * FFT_PITCH;
+      const double2 a = q[i], c = q[j];
+      const double2 cw = make_double2(c.x * w.x - c.y * w.y, c.x * w.y + c.y * w.x);
+      q[i] = make_double2(a.x + cw.x, a.y + cw.y);
+      q[j] = make_double2(a.x - cw.x, a.y - cw.y);
+    }
     __syncthreads();
   }
+  // transposed: output row e receives this CTA's eight values at columns row0 .. row0 + 7
+  const int r = t & (FFT_ROWS - 1);
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int e = t + 128 * k;
-    out[base + (size_t)e * 256 + row] = s[e];
+  for (int k = 0; k < 256 / (256 / FFT_ROWS); ++k) {
+    const int e = (t >> 3) + (256 / FFT_ROWS) * k;
+    out[base + (size_t)e * 256 + row0 + r] = s[r * FFT_PITCH + e];
   }
 }
 
@@ -239,8 +257,8 @@ int ccc_device_init(CccState& c, cudaStream_t stream, int* launches, std::string
   CCC_CUDA(cudaMemcpyAsync(c.d_bias.ptr, c.bias.data(), N_BINS2 * sizeof(float), cudaMemcpyHostToDevice, stream));
   CCC_CUDA(cudaMemcpyAsync(c.d_kf.ptr, &kf, sizeof kf, cudaMemcpyHostToDevice, stream));
   CCC_CUDA(cudaMemcpyAsync(tmp_f.ptr, c.filter.data(), N_BINS2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-  k_ccc_fft<0><<<dim3(256, 1), 128, 0, stream>>>(tmp_f.ptr, tmp_c.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
-  k_ccc_fft<1><<<dim3(256, 1), 128, 0, stream>>>(tmp_c.ptr, c.d_filter_fft.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
+  k_ccc_fft<0><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_f.ptr, tmp_c.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
+  k_ccc_fft<1><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_c.ptr, c.d_filter_fft.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
   CCC_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   CCC_CUDA(cudaStreamSynchronize(stream));  // host vectors and temporaries go out of scope
@@ -334,11 +352,11 @@ int ccc_white_balance(CccState& c, const Params& q, const FrameParams& fp, DevBu
     else k_ccc_hist<SRC_RGB><<<grid_h, 256, 0, stream>>>(fp, f0, xc, yc, log_tab, thr_hi, thr_lo, uv0, bin_size, counts);
     const long long nb = (long long)m * N_BINS2;
     k_ccc_weights<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(counts, c.d_weight.as<float>(), hist, nb);
-    const dim3 grid_f(256, m);
-    k_ccc_fft<0><<<grid_f, 128, 0, stream>>>(hist, sa, tw, nullptr);
-    k_ccc_fft<1><<<grid_f, 128, 0, stream>>>(sa, sb, tw, nullptr);
-    k_ccc_fft<2><<<grid_f, 128, 0, stream>>>(sb, sa, tw, c.d_filter_fft.as<double2>());
-    k_ccc_fft<3><<<grid_f, 128, 0, stream>>>(sa, sb, tw, nullptr);
+    const dim3 grid_f(256 / FFT_ROWS, m);
+    k_ccc_fft<0><<<grid_f, 256, 0, stream>>>(hist, sa, tw, nullptr);
+    k_ccc_fft<1><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr);
+    k_ccc_fft<2><<<grid_f, 256, 0, stream>>>(sb, sa, tw, c.d_filter_fft.as<double2>());
+    k_ccc_fft<3><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr);
     k_ccc_argmax<<<m, 1024, 0, stream>>>(sb, c.d_bias.as<float>(), uv_arg + f0);
     CCC_CUDA(cudaGetLastError());
     if (launches) *launches += 7;
