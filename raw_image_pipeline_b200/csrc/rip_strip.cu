@@ -33,7 +33,7 @@ bool strip_kernel_ok(uint32_t stages, const FrameParams& p) {
 
 bool strip_kernel_preferred(uint32_t stages) {
   // Measured (profiles/r2_strip_kernel.md): the strip kernel wins where the per-pixel arithmetic is light (debayer + gamma:
-  // 0.85 vs 1.02 ms per 64 x 12 MP); with the Lab / HSV stages the chain dominates and the tile kernel's synchronised warps
+  // 0.67 vs 1.02 ms per 64 x 12 MP); with the Lab / HSV stages the chain dominates and the tile kernel's synchronised warps
   // use the instruction cache better.
   return (stages & (ST_VIG | ST_ENH)) == 0;
 }

@@ -7,10 +7,16 @@
 //     lane) into a sliding three-row window held in registers (bayer_window.cuh);
 //   * each warp feeds itself: lane 0 has the TMA unit copy chunks of 4 rows x 160 bytes (strip + 16-byte halo columns,
 //     zero fill outside the frame) into the warp's private ring of three chunks, two chunks ahead of the arithmetic,
-//     completion signalled on the warp's own mbarriers.  A chunk is exactly four output rows: the loop body is the
-//     unrolled code of 4 (light stage sets) or 2 x 2 (heavy ones, to stay inside the instruction cache) rows, with the
-//     CFA-phase selectors of even and odd rows hoisted out of it.  There is no __syncthreads() in the steady state (only
-//     when the CTA moves on to another frame and swaps the per-frame white-balance table);
+//     completion signalled on the warp's own mbarriers.  A chunk is exactly four output rows: for the light stage sets
+//     the loop body is the straight-line code of those 4 rows with the CFA-phase selectors of even and odd rows hoisted
+//     out of it; for the heavy ones (Lab / HSV stages) it is a rolled row loop that flips the phase per row, to stay
+//     inside the instruction cache.  There is no __syncthreads() in the steady state (only when the CTA moves on to
+//     another frame and swaps the per-frame white-balance table);
+//   * the warp index is taken through a shuffle, so the compiler knows that ring slot, mbarrier addresses, TMA
+//     coordinates and staging bases are warp-uniform and keeps them in uniform registers (otherwise it re-broadcasts
+//     them in front of every TMA / mbarrier instruction: -22 integer-pipe instructions per row);
+//   * stage sets that are table lookups on bytes only (no colour calibration, Lab or HSV step) use ByteChain below:
+//     per-lane extraction selectors carry the frame-edge column replication and the 180-degree pixel order;
 //   * OpenCV's border rule (output row 0 = the interior formula at row 1, row H-1 = at row H-2) is served by two extra
 //     one-row units per strip and frame instead of special cases in the row loop;
 //   * the 4-byte intermediate (B,G,R,0 -- what the undistortion gather reads) leaves the registers directly: one
