@@ -28,6 +28,8 @@ StripGeom strip_geometry(const FrameParams& p) {
 bool strip_kernel_ok(uint32_t stages, const FrameParams& p) {
   // a colour calibration with a bias stays with the tile kernel (no bias add is compiled into the strip instantiations)
   if ((stages & ST_CC) && p.k.has_bias) return false;
+  // per-lane positions inside a frame are 32-bit byte offsets (output rows, vignetting-mask rows)
+  if ((long long)p.orows * p.out_pitch >= (1ll << 31) || (long long)p.rows * p.vig_pitch >= (1ll << 31)) return false;
   return !(stages & (ST_GAMMA | ST_VIG | ST_ENH)) || p.strip_tables != nullptr;
 }
 
