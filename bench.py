@@ -532,21 +532,22 @@ def run_latency(args, cfg):
     kernel_us_per_frame = float(sum(kms[:4])) / n * 1e3
 
     # ---- end to end: RawImagePipeline::apply() frame by frame, pageable numpy in, numpy out -------
-    def timed_apply(steps):
+    def timed_apply(steps, src=None):
+        src = frames if src is None else src
         lat = []
         outs = {}
         t_begin = time.perf_counter()
         for s in range(steps):
             for i in range(n):
                 t0 = time.perf_counter()
-                out = p.process(frames[i], enc)
+                out = p.process(src[i % len(src)], enc)
                 lat.append((time.perf_counter() - t0) * 1e6)
                 if s == steps - 1 and i in (0, n - 1):
                     outs[i] = out
         return lat, outs, time.perf_counter() - t_begin
 
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
-    e2e, lat_graph, lat_plain, outs, dt_e2e = None, None, None, {}, 0.0
+    e2e, lat_graph, lat_plain, lat_pinned, outs, dt_e2e = None, None, None, None, {}, 0.0
     if e2e_steps:
         timed_apply(1)  # warm-up: buffers, lazy tables, graph capture
         job.barrier()
@@ -560,6 +561,21 @@ def run_latency(args, cfg):
             timed_apply(1)
             lat_plain = percentiles(timed_apply(e2e_steps)[0])
             p._set_bool("apply/cuda_graph", True)
+        # SURVEY 8d config 4 "pinned double buffers": the camera frames arrive in page-locked buffers (two, used in turn)
+        pinned = [p.pinned_empty((rows, cols)) for _ in range(2)]
+        if all(a is not None for a in pinned):
+            def pinned_frames():
+                for i in range(n):
+                    pinned[i & 1][...] = frames[i]
+                    yield pinned[i & 1]
+            lat_p = []
+            for rep in range(1 + e2e_steps):  # pass 0 warms up (graph capture for the new buffer kind) and is not counted
+                for a in pinned_frames():
+                    t0 = time.perf_counter()
+                    p.process(a, enc)
+                    if rep:
+                        lat_p.append((time.perf_counter() - t0) * 1e6)
+            lat_pinned = percentiles(lat_p)
     per_stream = job.gather({"rank": rank, "latency_us": lat_graph, "mpix_per_s": (n * px * e2e_steps / dt_e2e / 1e6) if e2e_steps else None})
     if rank != 0:
         job.finish()
@@ -579,6 +595,7 @@ def run_latency(args, cfg):
         "latency_us": {"kernels_only_per_frame": kernel_us_per_frame,
                        "device_resident_call_per_frame": ms_total / args.steps / n * 1e3,
                        "apply_host_to_host_cuda_graph": lat_graph, "apply_host_to_host_no_graph": lat_plain,
+                       "apply_page_locked_input_buffers": lat_pinned,
                        "graph_replays": replays if e2e_steps else None},
         "streams": per_stream,
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * px) * world, "d2h_bytes_per_step": int(3 * n * px) * world,
