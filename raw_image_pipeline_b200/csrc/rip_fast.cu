@@ -393,6 +393,7 @@ constexpr int RT_STAGES = 2;
 constexpr int RT_CONSUMERS = 8, RT_THREADS = (RT_CONSUMERS + 1) * 32;
 constexpr int BOX_BYTES = BOX_W * BOX_H * 4;
 constexpr int RT_ROWS_WARP = RT_H / RT_CONSUMERS;  // consecutive tile rows owned by a warp, one per iteration
+constexpr int RT_FRAME_GROUP = 8;                  // frames that share one load of a tile's map entries
 static_assert(RT_W == 128 && RT_H % RT_CONSUMERS == 0, "a warp covers one 128-pixel tile row per iteration");
 
 struct RemapTileSmem {
@@ -420,19 +421,24 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;  // (a shuffle-derived, provably uniform warp index makes this kernel slower: 1.63 vs 1.47 ms)
   const int tiles_x = (P.ocols + RT_W - 1) / RT_W, tiles_y = (P.orows + RT_H - 1) / RT_H;
   const long long tiles_per_frame = (long long)tiles_x * tiles_y;
-  const long long total = tiles_per_frame * P.n_frames;
   if (tid == 0) {
     for (int i = 0; i < RT_STAGES; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], RT_CONSUMERS); }
     fence_mbar_init();
   }
   __syncthreads();
-  // Tiles are dealt round-robin: CTA c takes tiles c, c + G, c + 2G, ...  The CTAs then work on one band of adjacent tile
-  // rows at a time, so the rows that vertically adjacent boxes share are still in L2 when the next tile row asks for them.
+  // A unit of work is one tile for one GROUP of up to RT_FRAME_GROUP consecutive frames: the map is the same for every
+  // frame, so after the group's first frame a tile's 12 KB of map rows come from L2 / L1 instead of DRAM (the map was
+  // 40 % of this kernel's DRAM reads when every frame streamed it in again).
+  // Units are dealt round-robin, group-major: CTA c takes units c, c + G, c + 2G, ...  The CTAs then work on one band of
+  // adjacent tile rows of the same frames at a time, so the rows that vertically adjacent boxes share are still in L2
+  // when the next tile row asks for them.
+  const int n_groups = (P.n_frames + RT_FRAME_GROUP - 1) / RT_FRAME_GROUP;
+  const long long total = tiles_per_frame * n_groups;
   long long t = blockIdx.x;
   const long long t_end = total;
   TileStride ts;
   ts.init((int)gridDim.x, tiles_x, tiles_y);
-  TileIter ti;
+  TileIter ti;  // ti.frame counts frame groups here
   ti.init(t, tiles_x, tiles_per_frame);
 
   if (warp == RT_CONSUMERS) {
@@ -440,26 +446,30 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
     int buf = 0; uint32_t round = 0;
     for (; t < t_end; t += gridDim.x, ts.advance(ti, tiles_x, tiles_y)) {
       const int4 info = __ldg(P.tiles + (ti.ty * tiles_x + ti.tx));
-      // L2 prefetch of the tile's map rows (the consumers read them when they reach this tile)
+      // L2 prefetch of the tile's map rows (the consumers read them when they reach this unit)
       const int x0 = ti.tx * RT_W, y0 = ti.ty * RT_H;
       if (lane < RT_H)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.tmap + (size_t)(y0 + lane) * P.tmap_pitch + x0), "r"(RT_W * 4) : "memory");
-      if (round > 0) mbar_wait(&sm.empty[buf], (round - 1) & 1u);
-      if (lane == 0) {
-        sm.origin[buf][0] = info.x; sm.origin[buf][1] = info.y; sm.origin[buf][2] = info.z;
-        mbar_expect_tx(&sm.full[buf], BOX_BYTES);
-        tma_load_3d(sm.box[buf], &src_map, &sm.full[buf], info.x, info.y, ti.frame);
+      const int f0 = ti.frame * RT_FRAME_GROUP, f1 = min(f0 + RT_FRAME_GROUP, P.n_frames);
+      for (int f = f0; f < f1; ++f) {
+        if (round > 0) mbar_wait(&sm.empty[buf], (round - 1) & 1u);
+        if (lane == 0) {
+          sm.origin[buf][0] = info.x; sm.origin[buf][1] = info.y; sm.origin[buf][2] = info.z;
+          mbar_expect_tx(&sm.full[buf], BOX_BYTES);
+          tma_load_3d(sm.box[buf], &src_map, &sm.full[buf], info.x, info.y, f);
+        }
+        __syncwarp();
+        if (++buf == RT_STAGES) { buf = 0; ++round; }
       }
-      __syncwarp();
-      if (++buf == RT_STAGES) { buf = 0; ++round; }
     }
     return;
   }
 
   // ---- consumer warps ----
   // lane l, slot k: column x0 + l + 32 k of the iteration's row.  The four map entries of an iteration are loaded one
-  // iteration ahead (across tile boundaries too) from the tile-padded copy of the map (remap_tile_table): entries beyond
-  // the image edge point at the edge pixel's source position, so they need no special case (and are never stored).
+  // iteration ahead (across frame and unit boundaries too) from the tile-padded copy of the map (remap_tile_table):
+  // entries beyond the image edge point at the edge pixel's source position, so they need no special case (and are never
+  // stored).  Within a unit the same 12 KB of map rows are read once per frame: after the first frame they are L2 / L1 hits.
   auto map_load = [&](const TileIter& q, int i, uint32_t mm[4]) {
     const uint32_t* row = P.tmap + (size_t)(q.ty * RT_H + warp * RT_ROWS_WARP + i) * P.tmap_pitch + (q.tx * RT_W + lane);
 #pragma unroll
@@ -472,53 +482,58 @@ __global__ void __launch_bounds__(RT_THREADS, 3) k_remap_tile(const __grid_const
   for (; t < t_end; t += gridDim.x, ts.advance(ti, tiles_x, tiles_y)) {
     const int x0 = ti.tx * RT_W, yw = ti.ty * RT_H + warp * RT_ROWS_WARP;
     ts.advance(tn, tiles_x, tiles_y);
-    mbar_wait(&sm.full[buf], round & 1u);
-    const int bx0 = sm.origin[buf][0], by0 = sm.origin[buf][1];
-    const bool fast = (sm.origin[buf][2] & REMAP_TILE_FAST) != 0;
-    const uint32_t* box = sm.box[buf];
-    uint8_t* drow = P.dst + (long long)ti.frame * P.dst_frame_stride + (size_t)yw * P.dpitch + (size_t)(x0 + 4 * lane) * 3;
+    const int f0 = ti.frame * RT_FRAME_GROUP, f1 = min(f0 + RT_FRAME_GROUP, P.n_frames);
+#pragma unroll 1
+    for (int f = f0; f < f1; ++f) {
+      mbar_wait(&sm.full[buf], round & 1u);
+      const int bx0 = sm.origin[buf][0], by0 = sm.origin[buf][1];
+      const bool fast = (sm.origin[buf][2] & REMAP_TILE_FAST) != 0;
+      const uint32_t* box = sm.box[buf];
+      uint8_t* drow = P.dst + (long long)f * P.dst_frame_stride + (size_t)yw * P.dpitch + (size_t)(x0 + 4 * lane) * 3;
 #pragma unroll
-    for (int i = 0; i < RT_ROWS_WARP; ++i, drow += P.dpitch) {
-      uint32_t mn[4] = {0u, 0u, 0u, 0u};
-      if (i + 1 < RT_ROWS_WARP) map_load(ti, i + 1, mn);
-      else if (t + gridDim.x < t_end) map_load(tn, 0, mn);
-      const int ya = yw + i;
-      uint32_t p[4];
-      if (fast) {
-        // every tap of every pixel of this tile lies inside the box, and no entry is "far"
-        const uint32_t* rowbase = box + ((ya - by0) * BOX_W + (x0 + lane - bx0));
-        uint32_t tp[4][4];
+      for (int i = 0; i < RT_ROWS_WARP; ++i, drow += P.dpitch) {
+        uint32_t mn[4] = {0u, 0u, 0u, 0u};
+        if (i + 1 < RT_ROWS_WARP) map_load(ti, i + 1, mn);
+        else if (f + 1 < f1) map_load(ti, 0, mn);                  // same tile, next frame of the group
+        else if (t + gridDim.x < t_end) map_load(tn, 0, mn);       // next unit
+        const int ya = yw + i;
+        uint32_t p[4];
+        if (fast) {
+          // every tap of every pixel of this tile lies inside the box, and no entry is "far"
+          const uint32_t* rowbase = box + ((ya - by0) * BOX_W + (x0 + lane - bx0));
+          uint32_t tp[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t* q = rowbase + 32 * k + (remap_packed_dyi(mc[k]) * BOX_W + remap_packed_dxi(mc[k]));
-          tp[k][0] = q[0]; tp[k][1] = q[1]; tp[k][2] = q[BOX_W]; tp[k][3] = q[BOX_W + 1];
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t* q = rowbase + 32 * k + (remap_packed_dyi(mc[k]) * BOX_W + remap_packed_dxi(mc[k]));
+            tp[k][0] = q[0]; tp[k][1] = q[1]; tp[k][2] = q[BOX_W]; tp[k][3] = q[BOX_W + 1];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) p[k] = remap_blend_w(tp[k][0], tp[k][1], tp[k][2], tp[k][3], mc[k] & 31u, (mc[k] >> 10) & 0x7c0u);
+        } else {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)f * P.src_frame_stride);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int sx, sy;
+            remap_unpack_entry(mc[k], x0 + lane + 32 * k, ya, sx, sy);
+            p[k] = remap_tile_pixel_slow(P, box, bx0, by0, src, sx, sy);
+          }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = remap_blend_w(tp[k][0], tp[k][1], tp[k][2], tp[k][3], mc[k] & 31u, (mc[k] >> 10) & 0x7c0u);
-      } else {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.src + (long long)ti.frame * P.src_frame_stride);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int sx, sy;
-          remap_unpack_entry(mc[k], x0 + lane + 32 * k, ya, sx, sy);
-          p[k] = remap_tile_pixel_slow(P, box, bx0, by0, src, sx, sy);
+        for (int k = 0; k < 4; ++k) sm.px[warp][lane + 32 * k] = p[k];
+        __syncwarp();
+        const uint4 q = *reinterpret_cast<const uint4*>(&sm.px[warp][4 * lane]);  // 4 consecutive pixels
+        __syncwarp();
+        if (x0 + 4 * lane < P.ocols && ya < P.orows) {  // ocols % 4 == 0 (launcher): the quad is complete
+          uint32_t* d = reinterpret_cast<uint32_t*>(drow);
+          d[0] = prmt(q.x, q.y, 0x4210); d[1] = prmt(q.y, q.z, 0x5421); d[2] = prmt(q.z, q.w, 0x6542);
         }
-      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) sm.px[warp][lane + 32 * k] = p[k];
-      __syncwarp();
-      const uint4 q = *reinterpret_cast<const uint4*>(&sm.px[warp][4 * lane]);  // 4 consecutive pixels
-      __syncwarp();
-      if (x0 + 4 * lane < P.ocols && ya < P.orows) {  // ocols % 4 == 0 (launcher): the quad is complete
-        uint32_t* d = reinterpret_cast<uint32_t*>(drow);
-        d[0] = prmt(q.x, q.y, 0x4210); d[1] = prmt(q.y, q.z, 0x5421); d[2] = prmt(q.z, q.w, 0x6542);
+        for (int k = 0; k < 4; ++k) mc[k] = mn[k];
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) mc[k] = mn[k];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[buf]);  // this warp is done reading box[buf]
+      if (++buf == RT_STAGES) { buf = 0; ++round; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[buf]);  // this warp is done reading box[buf]
-    if (++buf == RT_STAGES) { buf = 0; ++round; }
   }
 }
 
@@ -707,9 +722,10 @@ cudaError_t launch_remap_tile(const RemapParams& p, int sm_count, cudaStream_t s
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
   }
-  const long long tiles = (long long)((p.ocols + RT_W - 1) / RT_W) * ((p.orows + RT_H - 1) / RT_H) * p.n_frames;
+  const long long units = (long long)((p.ocols + RT_W - 1) / RT_W) * ((p.orows + RT_H - 1) / RT_H) *
+                          ((p.n_frames + RT_FRAME_GROUP - 1) / RT_FRAME_GROUP);
   const long long cap = (long long)sm_count * occ;
-  const int grid = (int)(tiles < cap ? tiles : cap);
+  const int grid = (int)(units < cap ? units : cap);
   if (launches) ++*launches;
   k_remap_tile<<<grid, RT_THREADS, smem, stream>>>(p, sm);
   return cudaGetLastError();
