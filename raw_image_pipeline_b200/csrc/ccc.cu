@@ -92,9 +92,13 @@ __global__ void __launch_bounds__(256) k_ccc_weights(const unsigned* __restrict_
 //   MODE 3: complex input, inverse (unnormalised)
 constexpr int FFT_ROWS = 8;     // rows per CTA
 constexpr int FFT_PITCH = 257;  // double2 per shared row: the odd pitch makes the transposed read-out conflict-free
+// MODE 0 packs TWO frames into one complex transform: the histogram of frame 2j becomes the real part and that of frame
+// 2j + 1 (when it exists: `n_real` frames in all) the imaginary part of batch entry j.  The filter is real, so
+// IDFT2(DFT2(a + i b) * DFT2(f)) = conv(a, f) + i conv(b, f): after the four passes the real part of entry j is the
+// response of frame 2j and the imaginary part that of frame 2j + 1 -- half the transforms for the same sums.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_ccc_fft(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw,
-                                                 const double2* __restrict__ mul) {
+                                                 const double2* __restrict__ mul, int n_real) {
   __shared__ double2 s[FFT_ROWS * FFT_PITCH];
   __shared__ double2 s_tw[128];
   const int row0 = blockIdx.x * FFT_ROWS, t = threadIdx.x;
@@ -109,8 +113,9 @@ __global__ void __launch_bounds__(256) k_ccc_fft(const void* __restrict__ in, do
     const size_t idx = (size_t)(row0 + r) * 256 + t;
     double2 v;
     if (MODE == 0) {
-      v.x = (double)static_cast<const float*>(in)[base + idx];
-      v.y = 0.0;
+      const float* h = static_cast<const float*>(in) + 2 * base + idx;  // frames 2j and 2j + 1
+      v.x = (double)h[0];
+      v.y = 2 * (int)blockIdx.y + 1 < n_real ? (double)h[N_BINS2] : 0.0;
     } else {
       v = static_cast<const double2*>(in)[base + idx];
       if (MODE == 2) {
@@ -152,11 +157,12 @@ __global__ void __launch_bounds__(256) k_ccc_fft(const void* __restrict__ in, do
 __global__ void __launch_bounds__(1024) k_ccc_argmax(const double2* __restrict__ resp, const float* __restrict__ bias, int2* __restrict__ uv) {
   __shared__ double s_val[1024];
   __shared__ int s_idx[1024];
-  const double2* r = resp + (size_t)blockIdx.x * N_BINS2;
+  // frame f: entry f / 2 of the batch, real (even f) or imaginary (odd f) part -- see k_ccc_fft
+  const double* r = reinterpret_cast<const double*>(resp + (size_t)(blockIdx.x >> 1) * N_BINS2) + (blockIdx.x & 1);
   double best = -INFINITY;
   int best_i = 0x7fffffff;
   for (int i = threadIdx.x; i < N_BINS2; i += 1024) {
-    const double v = r[i].x * (1.0 / 65536.0) + (double)bias[i];
+    const double v = r[2 * i] * (1.0 / 65536.0) + (double)bias[i];
     if (v > best) { best = v; best_i = i; }  // increasing i per thread: strict > keeps the first
   }
   s_val[threadIdx.x] = best; s_idx[threadIdx.x] = best_i;
@@ -257,8 +263,8 @@ int ccc_device_init(CccState& c, cudaStream_t stream, int* launches, std::string
   CCC_CUDA(cudaMemcpyAsync(c.d_bias.ptr, c.bias.data(), N_BINS2 * sizeof(float), cudaMemcpyHostToDevice, stream));
   CCC_CUDA(cudaMemcpyAsync(c.d_kf.ptr, &kf, sizeof kf, cudaMemcpyHostToDevice, stream));
   CCC_CUDA(cudaMemcpyAsync(tmp_f.ptr, c.filter.data(), N_BINS2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-  k_ccc_fft<0><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_f.ptr, tmp_c.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
-  k_ccc_fft<1><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_c.ptr, c.d_filter_fft.as<double2>(), c.d_twiddle.as<double2>(), nullptr);
+  k_ccc_fft<0><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_f.ptr, tmp_c.as<double2>(), c.d_twiddle.as<double2>(), nullptr, 1);
+  k_ccc_fft<1><<<dim3(256 / FFT_ROWS, 1), 256, 0, stream>>>(tmp_c.ptr, c.d_filter_fft.as<double2>(), c.d_twiddle.as<double2>(), nullptr, 1);
   CCC_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   CCC_CUDA(cudaStreamSynchronize(stream));  // host vectors and temporaries go out of scope
@@ -352,15 +358,16 @@ int ccc_white_balance(CccState& c, const Params& q, const FrameParams& fp, DevBu
     else k_ccc_hist<SRC_RGB><<<grid_h, 256, 0, stream>>>(fp, f0, xc, yc, log_tab, thr_hi, thr_lo, uv0, bin_size, counts);
     const long long nb = (long long)m * N_BINS2;
     k_ccc_weights<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(counts, c.d_weight.as<float>(), hist, nb);
-    const dim3 grid_f(256 / FFT_ROWS, m);
-    k_ccc_fft<0><<<grid_f, 256, 0, stream>>>(hist, sa, tw, nullptr);
-    k_ccc_fft<1><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr);
-    k_ccc_fft<2><<<grid_f, 256, 0, stream>>>(sb, sa, tw, c.d_filter_fft.as<double2>());
-    k_ccc_fft<3><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr);
+    const dim3 grid_f(256 / FFT_ROWS, (m + 1) / 2);  // two frames per complex transform
+    k_ccc_fft<0><<<grid_f, 256, 0, stream>>>(hist, sa, tw, nullptr, m);
+    k_ccc_fft<1><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr, m);
+    k_ccc_fft<2><<<grid_f, 256, 0, stream>>>(sb, sa, tw, c.d_filter_fft.as<double2>(), m);
+    k_ccc_fft<3><<<grid_f, 256, 0, stream>>>(sa, sb, tw, nullptr, m);
     k_ccc_argmax<<<m, 1024, 0, stream>>>(sb, c.d_bias.as<float>(), uv_arg + f0);
     CCC_CUDA(cudaGetLastError());
     if (launches) *launches += 7;
-    c.d_last_response = sb + (size_t)(m - 1) * N_BINS2;
+    c.d_last_response = sb + (size_t)((m - 1) >> 1) * N_BINS2;
+    c.last_response_part = (m - 1) & 1;
   }
   const int temporal = q.wb_temporal_consistency ? 1 : 0;
   k_ccc_gains<<<temporal ? 1 : (n + 127) / 128, temporal ? 1 : 128, 0, stream>>>(uv_arg, n, temporal, c.pending_reset ? 1 : 0,

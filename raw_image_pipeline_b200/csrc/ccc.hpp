@@ -34,7 +34,8 @@ struct CccState {
   bool device_ready = false;
   // where the last call left its per-frame results (inside the caller's work buffer)
   const void* d_last_uv = nullptr;        // int2 (x, y) after temporal filtering
-  const void* d_last_response = nullptr;  // 256 x 256 double2, real part = 65536 * (conv), last frame
+  const void* d_last_response = nullptr;  // 256 x 256 double2 holding 65536 * (conv) of the last frame in its real (last_response_part == 0) or imaginary part
+  int last_response_part = 0;
   int last_n = 0;
 };
 

@@ -928,7 +928,7 @@ int rip_debug_table(rip_pipeline* p, const char* name, int rows, int cols, void*
     RIP_CUDA(p, cudaMemcpy(cplx.data(), p->ccc.d_last_response, cplx.size() * sizeof(double), cudaMemcpyDeviceToHost));
     data.resize(65536 * sizeof(double));
     double* o = reinterpret_cast<double*>(data.data());
-    for (int i = 0; i < 65536; ++i) o[i] = cplx[2 * i] * (1.0 / 65536.0);
+    for (int i = 0; i < 65536; ++i) o[i] = cplx[2 * i + p->ccc.last_response_part] * (1.0 / 65536.0);
   } else return p->fail(RIP_ERR_UNKNOWN_KEY, std::string("unknown table: ") + name);
   if (bytes) *bytes = data.size();
   if (!out || capacity < data.size()) return p->fail(RIP_ERR_BUFFER_TOO_SMALL, "table buffer too small");
