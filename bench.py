@@ -464,7 +464,7 @@ def run_batch(args, cfg):
         "roofline": {"bound": "hbm", "kernel": "k_fused<all stages, Bayer -> 4-byte intermediate>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": fused_ms,
-                     "note": "full chain at bit-exact parity is instruction-issue bound, not HBM bound (DESIGN.md)",
+                     "note": "full chain at bit-exact parity is bound by instruction issue (80 %) and the shared-memory pipe of its table lookups (78 %), not by HBM (DESIGN.md section 8)",
                      "other_kernels": other, "witness_debayer_gamma": witness},
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * rows * cols) * world,
                 "d2h_bytes_per_step": int(3 * n * rows * cols) * world, "steps": e2e_steps,
