@@ -287,3 +287,39 @@ def test_python_mirror_has_every_method_of_the_reference_pybind_module():
         import re
         defs = set(re.findall(r'\.def\("([a-z_0-9]+)"', open(ref).read()))
         assert defs == set(PYBIND_METHODS), defs ^ set(PYBIND_METHODS)
+
+
+def test_pinned_result_pool_bookkeeping():
+    """_PinnedPool (pipeline.py) with a stand-in allocator: buffers are reused, return when the last view dies, the pool
+    is bounded, and a closed pool frees what comes back (no GPU involved: the allocator is faked with malloc)."""
+    import ctypes, gc
+    from raw_image_pipeline_b200.pipeline import _PinnedPool
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p; libc.malloc.argtypes = [ctypes.c_size_t]; libc.free.argtypes = [ctypes.c_void_p]
+
+    class FakeLib:
+        live = set()
+        def rip_pinned_alloc(self, n, pp):
+            p = libc.malloc(n); pp._obj.value = p; self.live.add(p); return 0
+        def rip_pinned_free(self, p):
+            p = p if isinstance(p, int) else p.value
+            self.live.discard(p); libc.free(p); return 0
+
+    lib = FakeLib()
+    pool = _PinnedPool(lib)
+    a = pool.take(1000); a[:] = 7
+    view = a[10:20]
+    addr = a.ctypes.data
+    del a; gc.collect()
+    assert len(pool._free) == 0, "a live view keeps the buffer out of the pool"
+    assert int(view.sum()) == 70
+    del view; gc.collect()
+    assert len(pool._free) == 1
+    b = pool.take(500)                       # a smaller request reuses the buffer
+    assert b.ctypes.data == addr and b.size == 500
+    held = [pool.take(64) for _ in range(_PinnedPool.MAX_SLOTS + 3)]
+    assert sum(h is None for h in held) >= 3, "the pool is bounded; callers fall back to pageable arrays"
+    n_live = len(lib.live)
+    pool.close()
+    del b, held; gc.collect()
+    assert len(lib.live) == 0 and n_live > 0, "buffers coming back to a closed pool are freed"
