@@ -1176,25 +1176,34 @@ static int apply_host_chunks(rip_pipeline* p, const FrameGeom& g, const uint8_t*
   // consistency on, all chunks go through one slot so that they execute in order on one CUDA stream.
   const Params& q = p->hs.p;
   const int n_slots = (q.wb_enabled && q.wb_method == "ccc" && q.wb_temporal_consistency) ? 1 : kSlots;
-  int slot_i = 0, last_slot = -1, rc = RIP_OK;
-  for (;; slot_i = (slot_i + 1) % n_slots) {
-    Slot& s = p->slots[slot_i];
-    RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again; only then is the next chunk claimed
-    int f0 = 0, n = 0;
-    next_chunk(&f0, &n);
-    if (n <= 0) break;
-    last_slot = slot_i;
-    RIP_CUDA(p, s.in.reserve(in_frame * n));
-    RIP_CUDA(p, s.out.reserve(out_frame * n));
-    RIP_CUDA(p, cudaMemcpy2DAsync(s.in.ptr, in_frame, in + (size_t)f0 * in_frame_stride, in_frame_stride, in_frame, n,
-                                  cudaMemcpyHostToDevice, s.stream));
-    rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels * g.bytes_per_sample, in_frame, n, s.out.as<uint8_t>(), out_frame,
-                        nullptr, 0, false, s.stream, /*keep_bgr_color=*/false);
-    if (rc != RIP_OK) return rc;
-    RIP_CUDA(p, cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_frame_stride, s.out.ptr, out_frame, out_frame, n,
-                                  cudaMemcpyDeviceToHost, s.stream));
+  int last_slot = -1;
+  // the chunk loop proper; whatever it returns, no copy into or out of the caller's buffers may still be in flight when
+  // the entry point returns (the caller is free to release them), so every exit goes through the drain below
+  auto run = [&]() -> int {
+    for (int slot_i = 0;; slot_i = (slot_i + 1) % n_slots) {
+      Slot& s = p->slots[slot_i];
+      RIP_CUDA(p, cudaStreamSynchronize(s.stream));  // slot buffers free again; only then is the next chunk claimed
+      int f0 = 0, n = 0;
+      next_chunk(&f0, &n);
+      if (n <= 0) return RIP_OK;
+      last_slot = slot_i;
+      RIP_CUDA(p, s.in.reserve(in_frame * n));
+      RIP_CUDA(p, s.out.reserve(out_frame * n));
+      RIP_CUDA(p, cudaMemcpy2DAsync(s.in.ptr, in_frame, in + (size_t)f0 * in_frame_stride, in_frame_stride, in_frame, n,
+                                    cudaMemcpyHostToDevice, s.stream));
+      const int rc = process_device(p, s.scratch, g, s.in.as<uint8_t>(), (size_t)cols * channels * g.bytes_per_sample, in_frame, n,
+                                    s.out.as<uint8_t>(), out_frame, nullptr, 0, false, s.stream, /*keep_bgr_color=*/false);
+      if (rc != RIP_OK) return rc;
+      RIP_CUDA(p, cudaMemcpy2DAsync(out + (size_t)f0 * out_frame_stride, out_frame_stride, s.out.ptr, out_frame, out_frame, n,
+                                    cudaMemcpyDeviceToHost, s.stream));
+    }
+  };
+  int rc = run();
+  for (Slot& s : p->slots) {
+    const cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess && rc == RIP_OK) rc = p->cuda_fail(e, "cudaStreamSynchronize(slot stream)");
   }
-  for (Slot& s : p->slots) RIP_CUDA(p, cudaStreamSynchronize(s.stream));
+  if (rc != RIP_OK) return rc;
   if (last_slot >= 0 && q.wb_enabled && q.wb_method == "ccc") {  // the estimate of the last frame this pipeline saw, like after apply()
     Slot& s = p->slots[last_slot];
     if ((rc = ccc_fetch_last(p->ccc, s.scratch.gains, s.stream, p->last_error)) != RIP_OK) return rc;
