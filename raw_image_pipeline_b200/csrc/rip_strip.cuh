@@ -110,8 +110,7 @@ struct ByteChain {
   __device__ __forceinline__ uint32_t channel(uint32_t w, int j, taddr wb, const StripTables& t, bool has_wb) const {
     uint32_t v;
     if ((STAGES & ST_WB) && has_wb) {
-      v = lds_u8(taddr_byte_sel(wb, w, sel[j]));
-      if (STAGES & ST_GAMMA) v = lds_u8(t.gamma + v);
+      v = lds_u8(taddr_byte_sel(wb, w, sel[j]));  // the kernel stores gamma(white balance(v)) in the per-frame table when gamma is on
     } else if (STAGES & ST_GAMMA) {
       v = lds_u8(taddr_byte_sel(t.gamma, w, sel[j]));
     } else {
@@ -187,6 +186,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_strip(const __grid_constant_
       const float* src = P.wbf + (size_t)frame * 768;  // plain loads: written by a prior kernel
       for (int i = tid; i < 768; i += NT) {
         if (STAGES & ST_CC) reinterpret_cast<float*>(sm + SOFF_WBF)[i] = src[i];
+        else if (BYTE_ONLY && (STAGES & ST_GAMMA)) sm[SOFF_WB + i] = sm[SOFF_GAMMA + __float2int_rz(src[i])];  // ByteChain: gamma folded into the per-frame table, one lookup per channel
         else sm[SOFF_WB + i] = (uint8_t)__float2int_rz(src[i]);
       }
       __syncthreads();
