@@ -1010,6 +1010,11 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   if (!direct_in) RIP_CUDA(p, reserve_pinned(p->h_stage_in, p->h_stage_in_cap, pitch * rows));
   if (!direct_out) RIP_CUDA(p, reserve_pinned(p->h_stage_out, p->h_stage_out_cap, out_bytes));
   auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  // whatever happens below, no copy engine may still be reading `data` or writing `out` when this call returns
+  struct DrainOnExit {
+    cudaStream_t s; bool armed = true;
+    ~DrainOnExit() { if (armed) cudaStreamSynchronize(s); }
+  } drain{p->stream};
   const double t0 = now_us();
   // caller's image -> pinned staging (rows re-pitched to a multiple of 16 bytes: the TMA fast path)
   if (direct_in) RIP_CUDA(p, cudaMemcpyAsync(p->d_in.ptr, data, pitch * rows, cudaMemcpyHostToDevice, p->stream));
@@ -1068,6 +1073,7 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   p->ccc_pending_gains = nullptr;
   const double t2 = now_us();
   RIP_CUDA(p, cudaStreamSynchronize(p->stream));
+  drain.armed = false;
   const double t3 = now_us();
   if (!direct_out) CopyPool::get().copy(out, p->h_stage_out, out_bytes, /*pinned_side=*/1);
   const double t4 = now_us();
