@@ -548,7 +548,7 @@ def run_latency(args, cfg):
         return lat, outs, time.perf_counter() - t_begin
 
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
-    e2e, lat_graph, lat_plain, lat_pinned, outs, dt_e2e = None, None, None, None, {}, 0.0
+    e2e, lat_graph, lat_plain, lat_pinned, lat_registered, outs, dt_e2e = None, None, None, None, None, {}, 0.0
     if e2e_steps:
         timed_apply(1)  # warm-up: buffers, lazy tables, graph capture
         job.barrier()
@@ -577,6 +577,11 @@ def run_latency(args, cfg):
                     if rep:
                         lat_p.append((time.perf_counter() - t0) * 1e6)
             lat_pinned = percentiles(lat_p)
+        # opt-in: the library page-locks the caller's ordinary buffers the first time it sees them (a camera ring that is reused)
+        p._set_bool("apply/register_caller_buffers", True)
+        timed_apply(1)
+        lat_registered = percentiles(timed_apply(e2e_steps)[0])
+        p._set_bool("apply/register_caller_buffers", False)
     per_stream = job.gather({"rank": rank, "latency_us": lat_graph, "mpix_per_s": (n * px * e2e_steps / dt_e2e / 1e6) if e2e_steps else None})
     if rank != 0:
         job.finish()
@@ -597,6 +602,7 @@ def run_latency(args, cfg):
                        "device_resident_call_per_frame": ms_total / args.steps / n * 1e3,
                        "apply_host_to_host_cuda_graph": lat_graph, "apply_host_to_host_no_graph": lat_plain,
                        "apply_page_locked_input_buffers": lat_pinned,
+                       "apply_registered_caller_buffers_opt_in": lat_registered,
                        "graph_replays": replays if e2e_steps else None},
         "streams": per_stream,
         "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": int(n * px) * world, "d2h_bytes_per_step": int(3 * n * px) * world,

@@ -102,6 +102,9 @@ RIP_API int rip_reset_white_balance_temporal_consistency(rip_pipeline* p);  /* r
  *   instead of the packed fixed-point one), debug/force_gather_remap (undistortion gathers from global memory instead
  *   of the TMA-staged tile kernel); (int) debug/fused_kernel: 0 = the measured choice per stage set, 1 = tile kernel,
  *   2 = strip kernel.  None of them changes a single output byte.
+ * Extension (bool, default off): apply/register_caller_buffers -- rip_apply page-locks (cudaHostRegister) the image and
+ *   output buffers it is handed, once per buffer, and then copies straight from / into them; for callers that cycle through
+ *   a fixed set of ordinary buffers.  The caller promises that such a buffer stays mapped while the pipeline lives.
  * Extension (bool): undistortion/rect_mask -- getRectMask() returns a real validity mask (u8, 255 where all four taps of
  *   the bilinear remap lie inside the source image) instead of the reference's never-written empty image.        */
 RIP_API int rip_set_bool(rip_pipeline* p, const char* key, int value);

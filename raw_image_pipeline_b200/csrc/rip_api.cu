@@ -226,6 +226,13 @@ struct rip_pipeline {
   GraphKey graph_key_full() const { GraphKey k = graph_key_partial(); return (graph_key.wb == scratch.wb.ptr && graph_key.color == scratch.color.ptr && graph_key.stats == scratch.stats.ptr) ? k : GraphKey(); }
   int graph_warm = 0;          // direct (un-captured) runs with the current key: lazy one-time initialisation happens there
   bool use_graph = true;       // "apply/cuda_graph"
+  // "apply/register_caller_buffers" (opt-in): rip_apply page-locks the caller's image / output buffers the first time it
+  // sees them (cudaHostRegister) and remembers them, so a caller that cycles through a fixed set of ordinary buffers (a
+  // camera ring, a reused cv::Mat) gets direct copies without allocating anything specially.  The caller promises that a
+  // registered buffer stays mapped while the pipeline lives (a freed-and-reused address would be DMA'd from stale pages).
+  bool register_caller_buffers = false;
+  struct Registered { const uint8_t* base; size_t bytes; };
+  std::vector<Registered> registered;
   uint64_t config_epoch = 1;   // bumped by every setter / loader
   long long graph_replays = 0;
   double apply_us[5] = {0, 0, 0, 0, 0};  // last rip_apply: copy-in, enqueue (launch), wait for the device, copy-out ("stats/apply_us")
@@ -666,6 +673,7 @@ void rip_destroy(rip_pipeline* p) {
       if (sp.b) cudaEventDestroy(sp.b);
     }
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    for (const auto& r : p->registered) cudaHostUnregister(const_cast<uint8_t*>(r.base));
     if (p->h_stage_in) cudaFreeHost(p->h_stage_in);
     if (p->h_stage_out) cudaFreeHost(p->h_stage_out);
     ccc_release(p->ccc);
@@ -701,6 +709,7 @@ int rip_set_bool(rip_pipeline* p, const char* key, int value) {
   else if (key_is(key, "debug/force_gather_remap")) p->force_gather_remap = v;
   else if (key_is(key, "undistortion/rect_mask")) p->emit_rect_mask = v;
   else if (key_is(key, "apply/cuda_graph")) p->use_graph = v;
+  else if (key_is(key, "apply/register_caller_buffers")) p->register_caller_buffers = v;
   else if (key_is(key, "debayer/enabled")) q.debayer_enabled = v;
   else if (key_is(key, "debayer/allow_16bit")) q.debayer_allow_16bit = v;
   else if (key_is(key, "flip/enabled")) q.flip_enabled = v;
@@ -973,6 +982,20 @@ static bool host_pointer_is_pinned(const void* ptr) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// "apply/register_caller_buffers": true when [ptr, ptr + bytes) is (now) page-locked
+static bool register_caller_buffer(rip_pipeline* p, const uint8_t* ptr, size_t bytes) {
+  for (const auto& r : p->registered)
+    if (ptr >= r.base && ptr + bytes <= r.base + r.bytes) return true;
+  const size_t kMax = 64;
+  if (p->registered.size() >= kMax) {  // forget the oldest
+    cudaHostUnregister(const_cast<uint8_t*>(p->registered.front().base));
+    p->registered.erase(p->registered.begin());
+  }
+  if (cudaHostRegister(const_cast<uint8_t*>(ptr), bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+  p->registered.push_back({ptr, bytes});
+  return true;
+}
+
 extern "C" {
 
 int rip_pinned_alloc(size_t bytes, void** ptr) {
@@ -1005,8 +1028,12 @@ int rip_apply(rip_pipeline* p, const uint8_t* data, int rows, int cols, int chan
   RIP_CUDA(p, p->d_out.reserve(out_bytes));
   // Page-locked caller buffers (rip_pinned_alloc, cudaHostAlloc, cudaHostRegister) are read / written by the copy engines
   // directly; pageable ones go through the pipeline's own pinned staging buffers.
-  const bool direct_in = step == pitch && host_pointer_is_pinned(data);
-  const bool direct_out = host_pointer_is_pinned(out);
+  bool direct_in = step == pitch && host_pointer_is_pinned(data);
+  bool direct_out = host_pointer_is_pinned(out);
+  if (p->register_caller_buffers) {
+    if (!direct_in && step == pitch) direct_in = register_caller_buffer(p, data, pitch * rows);
+    if (!direct_out) direct_out = register_caller_buffer(p, out, out_bytes);
+  }
   if (!direct_in) RIP_CUDA(p, reserve_pinned(p->h_stage_in, p->h_stage_in_cap, pitch * rows));
   if (!direct_out) RIP_CUDA(p, reserve_pinned(p->h_stage_out, p->h_stage_out_cap, out_bytes));
   auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

@@ -149,8 +149,9 @@ def test_pinned_and_pageable_buffers(oracle_built):
     pin_in = p.pinned_empty((rows, cols))
     assert pin_in is not None
     held = []
-    for mode in ("pageable-out", "pinned-out", "pinned-in"):
-        p.use_pinned_results = mode != "pageable-out"
+    for mode in ("pageable-out", "pinned-out", "pinned-in", "registered"):
+        p.use_pinned_results = mode not in ("pageable-out", "registered")
+        p._set_bool("apply/register_caller_buffers", mode == "registered")  # opt-in: the caller's ordinary buffers get page-locked once
         for i, f in enumerate(frames):
             src = f
             if mode == "pinned-in":
@@ -161,11 +162,16 @@ def test_pinned_and_pageable_buffers(oracle_built):
             held.append(out)   # results stay valid while the caller holds them, whatever later calls do
     for k, out in enumerate(held):
         assert_same(out, refs[k % len(frames)], f"held result {k}")
+    p._set_bool("apply/register_caller_buffers", False)
+    p.use_pinned_results = True
     # the pool has a bound: holding more results than it may pin falls back to pageable arrays, transparently
     many = [p.process(frames[0], "bayer_bggr8") for _ in range(p._pool.MAX_SLOTS + 4)]
     for out in many:
         assert_same(out, refs[0], "beyond the pool")
-    del many, held
     import gc
+    del many
     gc.collect()
     assert len(p._pool._free) >= 1
+    del p          # the pipeline goes first: buffers it registered are still mapped when it unregisters them
+    gc.collect()
+    del held
