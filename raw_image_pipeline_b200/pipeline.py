@@ -160,6 +160,12 @@ class RawImagePipeline:
         out = np.array(arr[:n.value], dtype=np.float64)
         return out.reshape(shape) if shape else out
 
+    def set_register_caller_buffers(self, enabled: bool):
+        """Opt-in ("apply/register_caller_buffers"): process()/apply() page-lock the image buffers they are handed the first
+        time they see them and copy straight from them afterwards -- for callers that cycle through a fixed set of arrays
+        (a camera ring).  Those arrays must stay alive (mapped) as long as this pipeline does."""
+        self._set_bool("apply/register_caller_buffers", enabled)
+
     def pinned_empty(self, shape, dtype=np.uint8) -> Optional[np.ndarray]:
         """An uninitialised array in page-locked memory from the pipeline's pool (None when the pool is exhausted): frames
         placed in such an array are uploaded by the copy engine directly, without the staging copy of pageable images."""
