@@ -986,11 +986,9 @@ static bool host_pointer_is_pinned(const void* ptr) {
 static bool register_caller_buffer(rip_pipeline* p, const uint8_t* ptr, size_t bytes) {
   for (const auto& r : p->registered)
     if (ptr >= r.base && ptr + bytes <= r.base + r.bytes) return true;
-  const size_t kMax = 64;
-  if (p->registered.size() >= kMax) {  // forget the oldest
-    cudaHostUnregister(const_cast<uint8_t*>(p->registered.front().base));
-    p->registered.erase(p->registered.begin());
-  }
+  // a bounded set and no eviction: this is for callers that cycle through a few buffers; a caller that keeps bringing new
+  // ones (registering costs far more than one staged copy) simply gets the staged path for everything past the 64th
+  if (p->registered.size() >= 64) return false;
   if (cudaHostRegister(const_cast<uint8_t*>(ptr), bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return false; }
   p->registered.push_back({ptr, bytes});
   return true;
